@@ -1,0 +1,55 @@
+# Builds libmorsi_cuda (sm_100a kernels + C ABI), libmorsi_compat (reference
+# signatures) and the `morsi` host program.  nvcc cross-compiles without a GPU.
+#   make            lib + compat (+ morsi CLI when the reference iio.c is reachable)
+#   make oracle     the CPU checker under oracle/ (test infrastructure)
+NVCC   ?= nvcc
+CC     ?= gcc
+REF    ?= /root/reference
+ARCH   := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+SRC    := imscript_b200/csrc
+OUT    := imscript_b200/lib
+OBJ    := build/obj
+
+CU_SRCS := $(wildcard $(SRC)/*.cu)
+CU_OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(CU_SRCS))
+HDRS    := $(wildcard $(SRC)/*.cuh) $(wildcard $(SRC)/*.h) include/morsi_cuda.h
+
+all: $(OUT)/libmorsi_cuda.so $(OUT)/libmorsi_compat.so cli
+
+$(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJ)/$*.ptxas.log || (cat $(OBJ)/$*.ptxas.log; false)
+
+$(OBJ)/element.o: $(SRC)/element.c $(HDRS)
+	@mkdir -p $(OBJ)
+	$(CC) -O2 -fPIC -Wall -c $< -o $@
+
+$(OUT)/libmorsi_cuda.so: $(CU_OBJS) $(OBJ)/element.o
+	@mkdir -p $(OUT)
+	$(NVCC) $(ARCH) -shared -o $@ $^ -lm
+
+$(OUT)/libmorsi_compat.so: $(SRC)/compat.c $(OUT)/libmorsi_cuda.so
+	$(CC) -O2 -fPIC -Wall -shared -o $@ $(SRC)/compat.c -L$(OUT) -lmorsi_cuda -Wl,-rpath,'$$ORIGIN'
+
+# The CLI keeps the reference's image I/O: iio.c is compiled from the reference
+# tree (never copied).  Where the tree is absent the prebuilt binary is kept.
+ifneq ($(wildcard $(REF)/src/iio.c),)
+cli: $(OUT)/morsi
+$(OBJ)/iio.o: $(REF)/src/iio.c
+	@mkdir -p $(OBJ)
+	$(CC) -O3 -w -c $< -o $@
+$(OUT)/morsi: $(SRC)/morsi_main.c $(OBJ)/iio.o $(OUT)/libmorsi_cuda.so
+	$(CC) -O2 -Wall -o $@ $(SRC)/morsi_main.c $(OBJ)/iio.o -L$(OUT) -lmorsi_cuda -lm -Wl,-rpath,'$$ORIGIN'
+else
+cli:
+	@echo "morsi CLI: $(REF)/src/iio.c absent, keeping prebuilt $(OUT)/morsi"
+endif
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf build $(OUT)
+
+.PHONY: all cli oracle clean

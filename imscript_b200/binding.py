@@ -1,0 +1,232 @@
+"""ctypes binding of include/morsi_cuda.h."""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OPS = ["erosion", "dilation", "median", "rank", "opening", "closing",
+       "gradient", "igradient", "egradient", "laplacian", "enhance", "blur",
+       "oscillation", "tophat", "bothat", "iblur", "eblur", "cblur"]   # src/morsi.c:510-527
+
+# every symbol include/morsi_cuda.h declares for libmorsi_cuda.so
+EXPORTED_SYMBOLS = [
+    "morsi_cuda_strerror", "morsi_cuda_last_error", "morsi_element_parse",
+    "morsi_build_disk", "morsi_build_dysk", "morsi_build_hrec", "morsi_build_vrec",
+    "morsi_build_drec", "morsi_build_Drec", "morsi_element_free", "morsi_operation_parse",
+    "morsi_operation_name", "morsi_element_describe", "morsi_cuda_device_count",
+    "morsi_cuda_init", "morsi_cuda_shutdown", "morsi_cuda_apply", "morsi_cuda_apply_device",
+    "morsi_cuda_apply_band_device", "morsi_cuda_halo_rows", "morsi_cuda_set_path",
+    "morsi_cuda_launch_count", "morsi_cuda_launch_count_reset", "morsi_cuda_malloc",
+    "morsi_cuda_free", "morsi_cuda_host_alloc", "morsi_cuda_host_free", "morsi_cuda_memcpy_h2d",
+    "morsi_cuda_memcpy_d2h", "morsi_cuda_memcpy_d2d", "morsi_cuda_sync", "morsi_cuda_synth",
+    "morsi_synth_host", "morsi_cuda_event_create", "morsi_cuda_event_record",
+    "morsi_cuda_event_elapsed_ms", "morsi_cuda_event_destroy",
+]
+COMPAT_SYMBOLS = ["morsi_" + o for o in OPS] + ["morsi_all", "build_disk"]
+
+_f32p = ctypes.POINTER(ctypes.c_float)
+_i32p = ctypes.POINTER(ctypes.c_int)
+_vp = ctypes.c_void_p
+
+
+class MorsiError(RuntimeError):
+    def __init__(self, code, what):
+        super().__init__(f"libmorsi_cuda error {code}: {what}")
+        self.code = code
+
+
+def lib_path(name="libmorsi_cuda.so"):
+    return os.path.join(HERE, "lib", name)
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library; raises if it has not been built
+    (python -c 'import __graft_entry__ as g; g.build()' or `make`)."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise MorsiError(-1, f"{path} is missing: build it with `make` (nvcc, sm_100a); "
+                                 "there is no CPU fallback")
+        L = ctypes.CDLL(path)
+        L.morsi_cuda_strerror.restype = ctypes.c_char_p
+        L.morsi_cuda_last_error.restype = ctypes.c_char_p
+        L.morsi_operation_name.restype = ctypes.c_char_p
+        L.morsi_operation_name.argtypes = [ctypes.c_int]
+        L.morsi_cuda_launch_count.restype = ctypes.c_long
+        L.morsi_element_parse.argtypes = [ctypes.c_char_p, ctypes.POINTER(_i32p)]
+        for k in ("disk", "dysk", "hrec", "vrec", "drec", "Drec"):
+            f = getattr(L, "morsi_build_" + k)
+            f.restype = _i32p
+            f.argtypes = [ctypes.c_float]
+        L.morsi_element_free.argtypes = [_i32p]
+        L.morsi_operation_parse.argtypes = [ctypes.c_char_p]
+        L.morsi_element_describe.argtypes = [_i32p, ctypes.c_char_p, ctypes.c_size_t]
+        L.morsi_cuda_apply.argtypes = [ctypes.c_int, _i32p, _vp, _vp,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.morsi_cuda_apply_device.argtypes = [ctypes.c_int, _i32p, _vp, _vp, ctypes.c_int,
+                                              ctypes.c_int, ctypes.c_int, _vp]
+        L.morsi_cuda_apply_band_device.argtypes = [ctypes.c_int, _i32p, _vp, ctypes.c_int, ctypes.c_int,
+                                                   _vp, ctypes.c_int, ctypes.c_int,
+                                                   ctypes.c_int, ctypes.c_int, _vp]
+        L.morsi_cuda_halo_rows.argtypes = [ctypes.c_int, _i32p, _i32p, _i32p]
+        L.morsi_cuda_malloc.argtypes = [ctypes.POINTER(_vp), ctypes.c_size_t]
+        L.morsi_cuda_free.argtypes = [_vp]
+        L.morsi_cuda_host_alloc.argtypes = [ctypes.POINTER(_vp), ctypes.c_size_t]
+        L.morsi_cuda_host_free.argtypes = [_vp]
+        for k in ("h2d", "d2h", "d2d"):
+            getattr(L, "morsi_cuda_memcpy_" + k).argtypes = [_vp, _vp, ctypes.c_size_t, _vp]
+        L.morsi_cuda_sync.argtypes = [_vp]
+        L.morsi_cuda_synth.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_uint, ctypes.c_int, _vp]
+        L.morsi_synth_host.restype = None
+        L.morsi_synth_host.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_uint, ctypes.c_int]
+        L.morsi_cuda_event_create.argtypes = [ctypes.POINTER(_vp)]
+        L.morsi_cuda_event_record.argtypes = [_vp, _vp]
+        L.morsi_cuda_event_elapsed_ms.argtypes = [_vp, _vp, ctypes.POINTER(ctypes.c_float)]
+        L.morsi_cuda_event_destroy.argtypes = [_vp]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        L = lib()
+        raise MorsiError(rc, f"{L.morsi_cuda_strerror(rc).decode()}: {L.morsi_cuda_last_error().decode()}")
+
+
+def _op(op):
+    return OPS.index(op) if isinstance(op, str) else int(op)
+
+
+def _e(e):
+    if isinstance(e, str):
+        e = parse_element(e)
+        if e is None:
+            raise MorsiError(1, "elements = cross, square ...")
+    e = np.ascontiguousarray(e, dtype=np.int32)
+    if e.ndim != 1 or e.size < 4 or e.size < 4 + 2 * int(e[0]):
+        raise MorsiError(1, "malformed structuring element list")
+    return e
+
+
+def _take(ptr):
+    if not ptr:
+        return None
+    n = 4 + 2 * ptr[0]
+    out = np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+    lib().morsi_element_free(ptr)
+    return out
+
+
+def parse_element(name):
+    """src/morsi.c:496-508 -> int32 list, or None where the reference errors out."""
+    p = _i32p()
+    rc = lib().morsi_element_parse(name.encode(), ctypes.byref(p))
+    return _take(p) if rc == 0 else None
+
+
+def build_element(kind, radius):
+    return _take(getattr(lib(), "morsi_build_" + kind)(radius))
+
+
+def parse_operation(name):
+    return lib().morsi_operation_parse(name.encode())
+
+
+def describe_element(e):
+    e = _e(e)
+    buf = ctypes.create_string_buffer(128)
+    check(lib().morsi_element_describe(e.ctypes.data_as(_i32p), buf, 128))
+    return buf.value.decode()
+
+
+def device_count():
+    return lib().morsi_cuda_device_count()
+
+
+def halo_rows(op, e):
+    e = _e(e)
+    up, down = ctypes.c_int(), ctypes.c_int()
+    check(lib().morsi_cuda_halo_rows(_op(op), e.ctypes.data_as(_i32p), ctypes.byref(up), ctypes.byref(down)))
+    return up.value, down.value
+
+
+def apply(op, e, x):
+    """Host arrays in, host array out: morsi_cuda_apply().  x is (h,w) or
+    (planes,h,w) float32 (planar, as iio_read_image_float_split returns it)."""
+    e = _e(e)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if x.ndim < 2:
+        raise MorsiError(1, "image must have at least 2 dimensions")
+    h, w = x.shape[-2:]
+    planes = int(np.prod(x.shape[:-2])) if x.ndim > 2 else 1
+    y = np.empty_like(x)
+    check(lib().morsi_cuda_apply(_op(op), e.ctypes.data_as(_i32p), x.ctypes.data, y.ctypes.data, w, h, planes))
+    return y
+
+
+class DeviceBuffer:
+    """A device allocation owned through the C ABI (morsi_cuda_malloc)."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        p = _vp()
+        check(lib().morsi_cuda_malloc(ctypes.byref(p), self.nbytes))
+        self.ptr = p.value
+
+    @classmethod
+    def from_host(cls, a):
+        a = np.ascontiguousarray(a)
+        b = cls(a.nbytes)
+        check(lib().morsi_cuda_memcpy_h2d(b.ptr, a.ctypes.data, a.nbytes, None))
+        check(lib().morsi_cuda_sync(None))
+        return b
+
+    def to_host(self, shape, dtype=np.float32):
+        out = np.empty(shape, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        check(lib().morsi_cuda_memcpy_d2h(out.ctypes.data, self.ptr, out.nbytes, None))
+        check(lib().morsi_cuda_sync(None))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().morsi_cuda_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def apply_device(op, e, d_x, d_y, w, h, planes=1, stream=None, sync=True):
+    e = _e(e)
+    px = d_x.ptr if isinstance(d_x, DeviceBuffer) else d_x
+    py = d_y.ptr if isinstance(d_y, DeviceBuffer) else d_y
+    check(lib().morsi_cuda_apply_device(_op(op), e.ctypes.data_as(_i32p), px, py, w, h, planes, stream))
+    if sync:
+        check(lib().morsi_cuda_sync(stream))
+
+
+def apply_band_device(op, e, d_x, x_row0, x_rows, d_y, y_row0, y_rows, w, h, stream=None, sync=True):
+    e = _e(e)
+    px = d_x.ptr if isinstance(d_x, DeviceBuffer) else d_x
+    py = d_y.ptr if isinstance(d_y, DeviceBuffer) else d_y
+    check(lib().morsi_cuda_apply_band_device(_op(op), e.ctypes.data_as(_i32p), px, x_row0, x_rows,
+                                             py, y_row0, y_rows, w, h, stream))
+    if sync:
+        check(lib().morsi_cuda_sync(stream))
+
+
+def synth_host(w, rows, row0=0, plane=0, seed=1, dist=0):
+    out = np.empty((rows, w), dtype=np.float32)
+    lib().morsi_synth_host(out.ctypes.data, w, rows, row0, plane, seed, dist)
+    return out

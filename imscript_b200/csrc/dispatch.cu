@@ -1,0 +1,155 @@
+// dispatch.cu -- picks a kernel family for (operation, element, image) and
+// runs the passes.  The GPU counterpart of the function-pointer dispatch and
+// composite wrappers of src/morsi.c:141-275,509-543.
+#include <cstdio>
+#include <cstdlib>
+
+#include "dispatch.cuh"
+#include "k_exact.cuh"
+
+OpPlan morsi_op_plan(int op)
+{
+	//                         stages tmin tmax a  b  epi          special
+	switch (op) {
+	case MORSI_EROSION:     return {1, 0, 0, 1, 0, EPI_A, 0};
+	case MORSI_DILATION:    return {1, 0, 0, 0, 1, EPI_B, 0};
+	case MORSI_MEDIAN:      return {1, 0, 0, 0, 0, EPI_A, 1};
+	case MORSI_RANK:        return {1, 0, 0, 0, 0, EPI_A, 2};
+	case MORSI_OPENING:     return {2, 1, 0, 0, 2, EPI_B, 0};
+	case MORSI_CLOSING:     return {2, 0, 1, 3, 0, EPI_A, 0};
+	case MORSI_GRADIENT:    return {1, 0, 0, 1, 1, EPI_B_SUB_A, 0};
+	case MORSI_IGRADIENT:   return {1, 0, 0, 1, 0, EPI_X_SUB_A, 0};
+	case MORSI_EGRADIENT:   return {1, 0, 0, 0, 1, EPI_B_SUB_X, 0};
+	case MORSI_LAPLACIAN:   return {1, 0, 0, 1, 1, EPI_LAP, 0};
+	case MORSI_ENHANCE:     return {1, 0, 0, 1, 1, EPI_ENH, 0};
+	case MORSI_BLUR:        return {1, 0, 0, 1, 1, EPI_BLUR, 0};
+	case MORSI_OSCILLATION: return {2, 1, 1, 3, 2, EPI_A_SUB_B, 0};
+	case MORSI_TOPHAT:      return {2, 1, 0, 0, 2, EPI_X_SUB_B, 0};
+	case MORSI_BOTHAT:      return {2, 0, 1, 3, 0, EPI_A_SUB_X, 0};
+	case MORSI_IBLUR:       return {1, 0, 0, 1, 0, EPI_IBLUR, 0};
+	case MORSI_EBLUR:       return {1, 0, 0, 0, 1, EPI_EBLUR, 0};
+	case MORSI_CBLUR:       return {1, 0, 0, 1, 1, EPI_CBLUR, 0};
+	}
+	return {0, 0, 0, 0, 0, 0, 0};
+}
+
+void morsi_element_compile(MorsiCtx *, DevElement *d)
+{
+	d->rowrun.ok = 0;
+	if (d->info.kind == MORSI_EK_ROWRUN || (d->info.kind == MORSI_EK_SMALL && d->info.reach > 0)) {
+		d->rowrun.ok = 1;
+		d->rowrun.reach = d->info.reach;
+		for (int k = 0; k <= 2 * d->info.reach; k++) d->rowrun.hw[k] = d->info.halfwidth[k];
+	}
+}
+
+static dim3 exact_grid(int w, int rows, int planes)
+{
+	unsigned gy = (unsigned)((rows + 7) / 8);
+	if (gy > 16384) gy = 16384;
+	return dim3((unsigned)((w + 31) / 32), gy, (unsigned)planes);
+}
+
+template <int EPI>
+static void launch_exact_t(const ExactArgs &a, int planes, cudaStream_t s)
+{
+	k_exact_minmax<EPI><<<exact_grid(a.w, a.y_rows, planes), dim3(32, 8), 0, s>>>(a);
+	morsi_count_launch(1);
+}
+
+static int launch_exact(int epi, const ExactArgs &a, int planes, cudaStream_t s)
+{
+	switch (epi) {
+#define C(E) case E: launch_exact_t<E>(a, planes, s); break;
+	C(EPI_A) C(EPI_B) C(EPI_B_SUB_A) C(EPI_X_SUB_A) C(EPI_B_SUB_X) C(EPI_LAP) C(EPI_ENH)
+	C(EPI_BLUR) C(EPI_A_SUB_B) C(EPI_X_SUB_B) C(EPI_A_SUB_X) C(EPI_IBLUR) C(EPI_EBLUR)
+	C(EPI_CBLUR) C(EPI_AB)
+#undef C
+	default: return morsi_set_error(MORSI_ERR_INVALID, "bad epilogue %d", epi);
+	}
+	MORSI_CU(cudaGetLastError());
+	return MORSI_OK;
+}
+
+// The order-preserving path for every operation: one or two passes of
+// k_exact_minmax, temporaries in the context workspace.  `gate` (device word)
+// makes every kernel a no-op unless it is non-zero.
+int morsi_run_exact(MorsiCtx *c, const DevElement *de, const MorsiJob &job, const int *gate)
+{
+	const OpPlan plan = morsi_op_plan(job.op);
+	const int w = job.w, h = job.h;
+	Band xb{job.x, job.x_row0, job.x_pstride};
+
+	if (plan.special) {
+		MedianArgs m;
+		m.x_src = xb; m.y = job.y; m.y_pstride = job.y_pstride;
+		m.y_row0 = job.y_row0; m.y_rows = job.y_rows; m.w = w; m.h = h;
+		m.offs = de->d_offs; m.n = de->n; m.gate = gate;
+		dim3 g = exact_grid(w, job.y_rows, job.planes);
+		if (plan.special == 1) k_exact_median<<<g, dim3(32, 8), 0, job.stream>>>(m);
+		else k_exact_rank<<<g, dim3(32, 8), 0, job.stream>>>(m);
+		morsi_count_launch(1);
+		MORSI_CU(cudaGetLastError());
+		return MORSI_OK;
+	}
+
+	ExactArgs a;
+	a.x_src = xb; a.w = w; a.h = h; a.offs = de->d_offs; a.n = de->n; a.gate = gate;
+	a.y2 = nullptr;
+	Band tmin{nullptr, 0, 0}, tmax{nullptr, 0, 0};
+	if (plan.stages == 2) {
+		// stage 1 over the output band grown by one reach, clipped to the image
+		const int up = de->n ? (de->info.ymin < 0 ? -de->info.ymin : 0) : 0;
+		const int dn = de->n ? (de->info.ymax > 0 ? de->info.ymax : 0) : 0;
+		int t0 = job.y_row0 - up; if (t0 < 0) t0 = 0;
+		long long t1 = (long long)job.y_row0 + job.y_rows + dn; if (t1 > h) t1 = h;
+		const int t_rows = (int)(t1 - t0);
+		const long long tps = (long long)w * t_rows;
+		const size_t bytes = (size_t)tps * job.planes * sizeof(float);
+		void *p0 = nullptr, *p1 = nullptr;
+		int rc = morsi_ws_get(c, job.lane, 0, bytes, &p0);
+		if (rc) return rc;
+		if (plan.t_min && plan.t_max) { rc = morsi_ws_get(c, job.lane, 1, bytes, &p1); if (rc) return rc; }
+		ExactArgs s1 = a;
+		s1.a_src = xb; s1.b_src = xb;
+		s1.y_row0 = t0; s1.y_rows = t_rows; s1.y_pstride = tps;
+		int epi1;
+		if (plan.t_min && plan.t_max) { s1.y = (float *)p0; s1.y2 = (float *)p1; epi1 = EPI_AB;
+			tmin = Band{(float *)p0, t0, tps}; tmax = Band{(float *)p1, t0, tps}; }
+		else if (plan.t_min) { s1.y = (float *)p0; epi1 = EPI_A; tmin = Band{(float *)p0, t0, tps}; }
+		else { s1.y = (float *)p0; epi1 = EPI_B; tmax = Band{(float *)p0, t0, tps}; }
+		rc = launch_exact(epi1, s1, job.planes, job.stream);
+		if (rc) return rc;
+	}
+	const Band *srcs[4] = {&xb, &xb, &tmin, &tmax};
+	a.a_src = *srcs[plan.a_from]; a.b_src = *srcs[plan.b_from];
+	a.y = job.y; a.y_pstride = job.y_pstride; a.y_row0 = job.y_row0; a.y_rows = job.y_rows;
+	return launch_exact(plan.epi, a, job.planes, job.stream);
+}
+
+int morsi_dispatch(MorsiCtx *c, const int *e, const MorsiJob &job)
+{
+	const DevElement *de = nullptr;
+	int rc = morsi_element_get(c, e, &de);
+	if (rc) return rc;
+	// temporaries of two-stage exact passes are sized by the plane batch: keep
+	// them below 2 GiB per slot by splitting the batch
+	const OpPlan plan = morsi_op_plan(job.op);
+	if (plan.stages == 2 && job.planes > 1) {
+		long long per_plane = (long long)job.w * (job.y_rows + 2LL * (de->info.ymax - de->info.ymin + 1)) * 4;
+		long long max_planes = (2LL << 30) / (per_plane > 0 ? per_plane : 1);
+		if (max_planes < 1) max_planes = 1;
+		if (job.planes > max_planes) {
+			for (int p0 = 0; p0 < job.planes; p0 += (int)max_planes) {
+				MorsiJob sub = job;
+				sub.planes = job.planes - p0 < max_planes ? job.planes - p0 : (int)max_planes;
+				sub.x = job.x + p0 * job.x_pstride;
+				sub.y = job.y + p0 * job.y_pstride;
+				rc = morsi_dispatch(c, e, sub);
+				if (rc) return rc;
+			}
+			return MORSI_OK;
+		}
+	}
+	return morsi_run_exact(c, de, job, nullptr);
+}

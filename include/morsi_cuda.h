@@ -1,0 +1,198 @@
+/*
+ * morsi_cuda.h -- C ABI of libmorsi_cuda, the B200 (sm_100a) implementation of
+ * imscript's `morsi` gray-scale morphology hot path.
+ *
+ * Every entry point names the reference interface it replaces (paths relative
+ * to the reference root, mnhrdt/imscript).  Plain C: pointers, ints, sizes.
+ * There is no CPU fallback: without a usable CUDA device every compute call
+ * returns MORSI_ERR_NO_DEVICE / MORSI_ERR_CUDA.
+ *
+ * Data contract (src/morsi.c:34,66,543; src/iio.h:42-43): IEEE float32,
+ * planar, plane k at x + k*w*h, sample (i,j) of a plane at i + j*w, x fastest.
+ * A structuring element is the reference's int list (src/morsi.c:48-54):
+ * e[0]=count, e[1]=flags(0), (e[2],e[3])=centre, then (dx,dy) pairs from e[4];
+ * neighbour k of (i,j) is (i-e[2]+e[2k+4], j-e[3]+e[2k+5]).  Arbitrary lists
+ * (non-zero centre, repeats, any order) are legal: that is the reference's
+ * "user-defined mask" mechanism (src/ftr/webcam/corrview.c:37).
+ */
+#ifndef MORSI_CUDA_H
+#define MORSI_CUDA_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Operations, in the dispatcher order of src/morsi.c:510-527. */
+enum morsi_op {
+	MORSI_EROSION = 0,  /* src/morsi.c:56-68   */
+	MORSI_DILATION,     /* src/morsi.c:70-82   */
+	MORSI_MEDIAN,       /* src/morsi.c:103-120 */
+	MORSI_RANK,         /* src/morsi.c:122-139 */
+	MORSI_OPENING,      /* src/morsi.c:141-147 */
+	MORSI_CLOSING,      /* src/morsi.c:149-155 */
+	MORSI_GRADIENT,     /* src/morsi.c:157-167 */
+	MORSI_IGRADIENT,    /* src/morsi.c:169-176 */
+	MORSI_EGRADIENT,    /* src/morsi.c:178-185 */
+	MORSI_LAPLACIAN,    /* src/morsi.c:187-197 */
+	MORSI_ENHANCE,      /* src/morsi.c:199-206 */
+	MORSI_BLUR,         /* src/morsi.c:208-215 */
+	MORSI_OSCILLATION,  /* src/morsi.c:217-227 */
+	MORSI_TOPHAT,       /* src/morsi.c:229-236 */
+	MORSI_BOTHAT,       /* src/morsi.c:238-245 */
+	MORSI_IBLUR,        /* src/morsi.c:247-254 */
+	MORSI_EBLUR,        /* src/morsi.c:256-263 */
+	MORSI_CBLUR,        /* src/morsi.c:265-275 */
+	MORSI_OP_COUNT
+};
+
+/* Return codes (the reference functions return void and exit(-1) through
+ * fail(), src/xmalloc.c:18-27, src/fail.c:65-81; here errors come back). */
+enum morsi_status {
+	MORSI_OK = 0,
+	MORSI_ERR_INVALID = 1,    /* bad op / NULL pointer / non-positive size / bad element */
+	MORSI_ERR_NO_DEVICE = 2,  /* no CUDA device: there is no CPU fallback */
+	MORSI_ERR_CUDA = 3,       /* a CUDA call failed; see morsi_cuda_last_error() */
+	MORSI_ERR_OOM = 4,        /* device or host allocation failed */
+	MORSI_ERR_TOO_LARGE = 5,  /* w*h*planes beyond what one call supports */
+	MORSI_ERR_COMM = 6        /* halo exchange / peer access failure */
+};
+
+const char *morsi_cuda_strerror(int status);
+/* Detail of the last failure on the calling thread ("" if none). */
+const char *morsi_cuda_last_error(void);
+
+/* ---- structuring elements and names (host side, no GPU needed) ---------- */
+
+/* Element-name grammar of src/morsi.c:484-485,496-508 ("cross", "square",
+ * "diskR", "dyskR", "hrecR", "vrecR", "drecR", "DrecR", with the reference's
+ * strspn() semantics).  On success *e receives a malloc'd list to be released
+ * with morsi_element_free(); returns MORSI_ERR_INVALID where the reference
+ * prints "elements = cross, square ..." and exits 1. */
+int morsi_element_parse(const char *name, int **e);
+/* The builders of src/morsi.c:313-417; NULL when radius <= 1 (or NaN). */
+int *morsi_build_disk(float radius);   /* src/morsi.c:313-330 */
+int *morsi_build_dysk(float radius);   /* src/morsi.c:332-349 */
+int *morsi_build_hrec(float radius);   /* src/morsi.c:351-366 */
+int *morsi_build_vrec(float radius);   /* src/morsi.c:368-383 */
+int *morsi_build_drec(float radius);   /* src/morsi.c:385-400 */
+int *morsi_build_Drec(float radius);   /* src/morsi.c:402-417 */
+void morsi_element_free(int *e);
+/* Operation-name table of src/morsi.c:509-527: index, or -1 if unknown. */
+int morsi_operation_parse(const char *name);
+const char *morsi_operation_name(int op);
+
+/* How the element compiler classified a list (for reports and tests):
+ * writes a short tag such as "small3x3", "rowrun", "direct" into buf. */
+int morsi_element_describe(const int *e, char *buf, size_t buflen);
+
+/* ---- device management -------------------------------------------------- */
+
+int morsi_cuda_device_count(void);
+/* Select the device used by the calling process for the *_device entry
+ * points and create its context (stream, workspace).  Optional: the first
+ * compute call does morsi_cuda_init(0) implicitly. */
+int morsi_cuda_init(int device);
+void morsi_cuda_shutdown(void);
+
+/* ---- the hot path -------------------------------------------------------- */
+
+/* Replaces the channel loop of src/morsi.c:539-543 around
+ * operation(y+k*w*h, x+k*w*h, w, h, e): HOST pointers in, HOST pointers out,
+ * synchronous.  Copies to the device(s), runs the sm_100a kernels, copies back.
+ * When MORSI_CUDA_DEVICES=N (N>1) is set, planes (or, for a single plane, row
+ * bands with halo rows exchanged over peer copies) are spread over N devices. */
+int morsi_cuda_apply(int op, const int *e, const float *x, float *y,
+		int w, int h, int planes);
+
+/* Same computation on DEVICE-resident planar data (row pitch = w), enqueued on
+ * `stream` (a cudaStream_t; NULL = the context's stream) of the current
+ * device, asynchronous. d_x and d_y must not overlap. */
+int morsi_cuda_apply_device(int op, const int *e, const float *d_x, float *d_y,
+		int w, int h, int planes, void *stream);
+
+/* Row-band form, for images sharded across devices or streamed in tiles.
+ * The plane has `h` rows in total; d_x holds its rows [x_row0, x_row0+x_rows),
+ * d_y receives rows [y_row0, y_row0+y_rows) (row pitch w in both).  Rows outside
+ * [0,h) are absent (the NaN rule of src/morsi.c:30-35); every in-image row
+ * within morsi_cuda_halo_rows(op,e) of the output band must be present in d_x,
+ * otherwise MORSI_ERR_INVALID. */
+int morsi_cuda_apply_band_device(int op, const int *e,
+		const float *d_x, int x_row0, int x_rows,
+		float *d_y, int y_row0, int y_rows,
+		int w, int h, void *stream);
+/* Input rows needed above (*up) and below (*down) an output band. */
+int morsi_cuda_halo_rows(int op, const int *e, int *up, int *down);
+
+/* Force a kernel family: 0 = automatic, 1 = order-preserving exact kernels
+ * only (the signed-zero-safe path), 2 = fast kernels without the signed-zero
+ * re-run (benchmark use).  Also settable with MORSI_CUDA_PATH=auto|exact|fast. */
+int morsi_cuda_set_path(int path);
+
+/* Number of kernels launched by this process since the last reset, and a
+ * reset; bench.py reports it as "gpu_launches". */
+long morsi_cuda_launch_count(void);
+void morsi_cuda_launch_count_reset(void);
+
+/* ---- plumbing for callers without a CUDA runtime of their own ----------- */
+
+int morsi_cuda_malloc(void **d_ptr, size_t bytes);
+int morsi_cuda_free(void *d_ptr);
+int morsi_cuda_host_alloc(void **h_ptr, size_t bytes);   /* pinned */
+int morsi_cuda_host_free(void *h_ptr);
+int morsi_cuda_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes, void *stream);
+int morsi_cuda_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes, void *stream);
+int morsi_cuda_memcpy_d2d(void *d_dst, const void *d_src, size_t bytes, void *stream);
+int morsi_cuda_sync(void *stream);
+/* Device-side synthetic image of SURVEY.md 8(d): distribution 0 = uniform
+ * [0,1) on a 2^-24 grid, 1 = integers 0..255, 2 = distribution 0 with NaN /
+ * +-Inf / +-0 sprinkled in; value = f(seed, plane, row, column), so bands and
+ * crops of the same image can be generated independently. */
+int morsi_cuda_synth(float *d_x, int w, int rows, int row0, int plane,
+		unsigned seed, int distribution, void *stream);
+void morsi_synth_host(float *x, int w, int rows, int row0, int plane,
+		unsigned seed, int distribution);
+/* Events, for timing on the launching stream. */
+int morsi_cuda_event_create(void **ev);
+int morsi_cuda_event_record(void *ev, void *stream);
+int morsi_cuda_event_elapsed_ms(void *ev_start, void *ev_stop, float *ms);
+int morsi_cuda_event_destroy(void *ev);
+
+/* ---- the reference's own function signatures ----------------------------
+ * Drop-in for library-style callers of src/morsi.c (corrview.c:37-38,71-72):
+ * same names, same arguments, host pointers; on failure they print one line
+ * to stderr and exit(-1), the reference's fail() convention.  They live in
+ * libmorsi_compat so the names do not clash inside the oracle tests. */
+void morsi_erosion(float *y, float *x, int w, int h, int *e);
+void morsi_dilation(float *y, float *x, int w, int h, int *e);
+void morsi_median(float *y, float *x, int w, int h, int *e);
+void morsi_rank(float *y, float *x, int w, int h, int *e);
+void morsi_opening(float *y, float *x, int w, int h, int *e);
+void morsi_closing(float *y, float *x, int w, int h, int *e);
+void morsi_gradient(float *y, float *x, int w, int h, int *e);
+void morsi_igradient(float *y, float *x, int w, int h, int *e);
+void morsi_egradient(float *y, float *x, int w, int h, int *e);
+void morsi_laplacian(float *y, float *x, int w, int h, int *e);
+void morsi_enhance(float *y, float *x, int w, int h, int *e);
+void morsi_blur(float *y, float *x, int w, int h, int *e);
+void morsi_oscillation(float *y, float *x, int w, int h, int *e);
+void morsi_tophat(float *y, float *x, int w, int h, int *e);
+void morsi_bothat(float *y, float *x, int w, int h, int *e);
+void morsi_iblur(float *y, float *x, int w, int h, int *e);
+void morsi_eblur(float *y, float *x, int w, int h, int *e);
+void morsi_cblur(float *y, float *x, int w, int h, int *e);
+/* src/morsi.c:278-310: NULL outputs are skipped. */
+void morsi_all(float *o_ero, float *o_dil, float *o_ope, float *o_clo,
+		float *o_grad, float *o_igrad, float *o_egrad,
+		float *o_lap, float *o_enh, float *o_str,
+		float *o_top, float *o_bot, float *x, int w, int h, int *e);
+int *build_disk(float radius);         /* src/morsi.c:313 (non-static there) */
+/* src/morsi.c:478: the CLI entry kept callable for the `im` multi-call
+ * binary (src/im.c:4-6); defined by the morsi host program, not the library. */
+int main_morsi(int c, char **v);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MORSI_CUDA_H */

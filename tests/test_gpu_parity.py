@@ -1,0 +1,151 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the
+golden vectors recorded from the reference.  Bit-exact for everything; NaNs are
+compared by class (payloads are platform noise)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import imscript_b200 as M
+from oracle import OPS, oracle
+from tests.golden.make_golden import adversarial_input, kat_input, sha
+
+pytestmark = pytest.mark.gpu
+
+
+def same_bits(a, b):
+    a = np.asarray(a, dtype=np.float32)
+    b = np.asarray(b, dtype=np.float32)
+    an, bn = np.isnan(a), np.isnan(b)
+    return a.shape == b.shape and np.array_equal(an, bn) and \
+        np.array_equal(a.view(np.uint32)[~an], b.view(np.uint32)[~bn])
+
+
+def assert_same(got, want, what):
+    if not same_bits(got, want):
+        bad = np.argwhere(~((got.view(np.uint32) == want.view(np.uint32)) | (np.isnan(got) & np.isnan(want))))
+        i = tuple(bad[0])
+        raise AssertionError(f"{what}: {len(bad)} samples differ, first at {i}: got {got[i]!r} want {want[i]!r}")
+
+
+def test_known_answers(golden_dir):
+    kat = json.load(open(os.path.join(golden_dir, "kat_9_7.json")))
+    gold_e = json.load(open(os.path.join(golden_dir, "elements.json")))
+    x = kat_input()
+    for key, (h, s, y00, ymid) in kat["cases"].items():
+        name, op = key.split()
+        y = M.apply(op, np.array(gold_e[name], dtype=np.int32), x)
+        assert sha(y) == h, key
+
+
+@pytest.mark.parametrize("path", [0, 1])
+def test_adversarial_golden(golden_dir, path):
+    z = np.load(os.path.join(golden_dir, "adversarial.npz"))
+    x = z["x"]
+    M.lib().morsi_cuda_set_path(path)
+    try:
+        for name in [k[2:] for k in z.files if k.startswith("e:")]:
+            e = z["e:" + name]
+            gold = z["y:" + name].view(np.float32)
+            for k, op in enumerate(OPS):
+                assert_same(M.apply(op, e, x), gold[k], f"{name} {op} path={path}")
+    finally:
+        M.lib().morsi_cuda_set_path(0)
+
+
+SHAPES = [(1, 1), (1, 37), (41, 1), (2, 3), (7, 5), (33, 65), (64, 64), (97, 131), (130, 257)]
+ELEMENTS = ["cross", "square", "disk2.5", "disk3", "disk4.2", "disk5", "disk7", "dysk4", "hrec6",
+            "vrec3", "drec4", "Drec3", "hrec40", "vrec37"]
+
+
+@pytest.mark.parametrize("dist", [0, 1, 2])
+def test_vs_oracle_shapes_elements_ops(dist):
+    """ragged / tiny / degenerate shapes x every element family x all 18 ops"""
+    o = oracle()
+    for si, (h, w) in enumerate(SHAPES):
+        x = M.synth_host(w, h, seed=10 + si, dist=dist)
+        for name in ELEMENTS:
+            if h * w > 4000 and name in ("hrec40", "vrec37", "disk7") and dist == 1:
+                continue
+            e = o.element(name)
+            for op in OPS:
+                if op in ("median", "rank") and h * w > 9000 and e[0] > 60:
+                    continue
+                assert_same(M.apply(op, e, x), o.apply(op, e, x), f"{name} {op} {w}x{h} dist={dist}")
+
+
+def test_multi_plane_and_user_lists():
+    o = oracle()
+    x = np.stack([M.synth_host(50, 40, plane=p, seed=4, dist=2 if p == 1 else 0) for p in range(3)])
+    for e in ([4, 0, 1, -1, 0, 0, 2, 1, -1, 0, 3, -2], [6, 0, 0, 0, 1, 0, 1, 0, -1, 0, 0, 2, 0, 2, -2, -1],
+              [1, 0, 0, 0, 2, 1], [0, 0, 0, 0], o.element("disk3")):
+        e = np.array(e, dtype=np.int32)
+        for op in OPS:
+            assert_same(M.apply(op, e, x), o.apply(op, e, x), f"user {list(e[:6])} {op}")
+
+
+def test_device_and_band_entry_points():
+    """1-device result == the same image processed as row bands"""
+    o = oracle()
+    h, w = 150, 70
+    x = M.synth_host(w, h, seed=9, dist=2)
+    dx = M.DeviceBuffer.from_host(x)
+    dy = M.DeviceBuffer(x.nbytes)
+    for name, op in [("disk5", "tophat"), ("cross", "gradient"), ("disk3", "median"), ("dysk4", "oscillation"),
+                     ("disk7", "closing"), ("square", "rank"), ("vrec9", "opening")]:
+        e = o.element(name)
+        want = o.apply(op, e, x)
+        M.apply_device(op, e, dx, dy, w, h)
+        assert_same(dy.to_host((h, w)), want, f"device {name} {op}")
+        up, down = M.halo_rows(op, e)
+        got = np.empty_like(x)
+        for b0, b1 in [(0, 40), (40, 41), (41, 110), (110, 150)]:
+            i0, i1 = max(0, b0 - up), min(h, b1 + down)
+            bx = M.DeviceBuffer.from_host(x[i0:i1])
+            by = M.DeviceBuffer((b1 - b0) * w * 4)
+            M.apply_band_device(op, e, bx, i0, i1 - i0, by, b0, b1 - b0, w, h)
+            got[b0:b1] = by.to_host((b1 - b0, w))
+        assert_same(got, want, f"bands {name} {op}")
+    with pytest.raises(M.MorsiError):   # halo rows missing
+        M.apply_band_device("tophat", "disk5", dx, 10, 20, dy, 10, 20, w, h)
+
+
+def test_reference_signature_mirror():
+    o = oracle()
+    w, h = 31, 17
+    x = M.synth_host(w, h, seed=2)
+    e = M.morsi.build_disk(5.1)                       # corrview.c:37
+    y = np.empty(w * h, np.float32)
+    M.morsi.morsi_bothat(y, x.reshape(-1), w, h, e)   # corrview.c:38
+    assert_same(y.reshape(h, w), o.apply("bothat", e, x), "morsi_bothat")
+    outs = [np.empty(w * h, np.float32) if k % 2 == 0 else None for k in range(12)]
+    M.morsi.morsi_all(*outs, x.reshape(-1), w, h, e)
+    for out, op in zip(outs, ["erosion", "dilation", "opening", "closing", "gradient", "igradient",
+                              "egradient", "laplacian", "enhance", "oscillation", "tophat", "bothat"]):
+        if out is not None:
+            assert_same(out.reshape(h, w), o.apply(op, e, x), "morsi_all " + op)
+
+
+def test_full_size_properties():
+    """BASELINE config sizes through size-independent properties (the oracle
+    would need hours): duality, extensivity, idempotence, linearity under
+    monotone maps, crop-vs-oracle spot checks."""
+    o = oracle()
+    w = h = 4096
+    x = M.synth_host(w, h, seed=2, dist=0)
+    e = o.element("disk7")
+    ope = M.apply("opening", e, x)
+    clo = M.apply("closing", e, x)
+    assert np.all(ope <= x) and np.all(clo >= x)                       # anti-/extensive
+    assert np.array_equal(M.apply("opening", e, ope), ope)             # idempotent
+    assert np.array_equal(-M.apply("opening", e, -x), clo)             # duality (no zeros in -x? zeros are rare)
+    assert np.array_equal(M.apply("tophat", e, x), x - ope)
+    assert np.array_equal(M.apply("bothat", e, x), clo - x)
+    for (r0, c0) in [(0, 0), (2000, 1500), (h - 96, w - 96), (0, w - 96)]:
+        # window = crop grown by 2*reach where the image allows: artificial window
+        # edges are then >= 2*reach away from the crop, real image edges coincide
+        y0, x0 = max(0, r0 - 12), max(0, c0 - 12)
+        win = x[y0:min(h, r0 + 96 + 12), x0:min(w, c0 + 96 + 12)]
+        want = o.apply("opening", e, win)[r0 - y0:r0 - y0 + 96, c0 - x0:c0 - x0 + 96]
+        assert_same(ope[r0:r0 + 96, c0:c0 + 96], want, f"opening crop at {(r0, c0)}")
