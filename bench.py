@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- morsi hot-path benchmark (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl ours|reference]
+
+Prints ONE JSON line.  A "step" is one pass of the hot path over one batch of
+synthetic input; the default workload is BASELINE.json configs[1] ("c2":
+disk7 opening AND closing of a 4096x4096 float32 RGB image => 2 x 3 x 4096^2
+samples per step per GPU).  `value` is whole-job Msample/s ("Mpixel/s" in the
+reference's vocabulary: one pixel = one float32 sample of one plane) with the
+input resident in HBM; `e2e` is the same metric through morsi_cuda_apply()
+with pinned HOST buffers, copies inside the timed region.
+
+Under torchrun (N>1) every rank processes its own frames (no data-path
+collective, "weak") except for --workload c4, where one 40000x40000 plane is
+row-band sharded and halo rows are exchanged between ranks every step
+("strong").  torch is used for the process group only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (element, [ops], w, h, planes, seed, description)
+    "c1": ("square", ["erosion"], 1024, 1024, 1, 1, "square erosion 1024x1024x1 (BASELINE configs[0])"),
+    "c2": ("disk7", ["opening", "closing"], 4096, 4096, 3, 2,
+           "disk7 opening+closing 4096x4096x3 (BASELINE configs[1])"),
+    "c3": ("disk5", ["median"], 8192, 8192, 1, 3, "disk5 median 8192x8192x1 (BASELINE configs[2])"),
+    "c4": ("disk15", ["tophat"], 40000, 40000, 1, 4,
+           "disk15 tophat 40000x40000x1, row-band sharded (BASELINE configs[3])"),
+    "c5": ("cross", ["gradient"], 1920, 1080, 3 * 64, 5,
+           "cross gradient, 64 RGB 1920x1080 frames per GPU per step (chunk of BASELINE configs[4])"),
+}
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        out = self.proc.communicate()[0]
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return world, rank, local, dist, torch
+    return 1, 0, 0, None, None
+
+
+# ----------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation on the host cores
+# ----------------------------------------------------------------------------
+def reference_sample_shape(name, big):
+    """A bounded crop of the workload: ~10-15 s of single-thread CPU work for the
+    cpu_baseline leg (big), ~2-3 s per step for the --impl reference arm."""
+    if big:
+        return {"c1": (1024, 1024), "c2": (2048, 1536), "c3": (2048, 1536), "c4": (1536, 1024),
+                "c5": (1920, 1080)}[name]
+    return {"c1": (1024, 1024), "c2": (1024, 768), "c3": (1024, 768), "c4": (768, 512),
+            "c5": (1920, 1080)}[name]
+
+
+def run_reference_once(name, threads, seed_offset=0, big=False):
+    """All `threads` host threads run the reference (oracle/_ref, else the oracle
+    port) on their own crop, the reference's own parallelism doctrine
+    (doc/misc/optimization.txt:43-49: several single-threaded programs at once).
+    Returns (samples processed, seconds, kind)."""
+    import imscript_b200 as M
+    from oracle import oracle as get_oracle
+    from oracle.oracle import Reference
+    element, ops, w, h, planes, seed, _ = WORKLOADS[name]
+    cw, ch = reference_sample_shape(name, big)
+    o = get_oracle()
+    e = o.element(element)
+    kind = "port"
+    impl = o
+    if os.path.exists(Reference.path):
+        from oracle import reference as get_ref
+        impl, kind = get_ref(), "reference"
+    crops = [M.synth_host(cw, ch, row0=(h - ch) // 2, plane=t, seed=seed + seed_offset) for t in range(threads)]
+
+    def work(t):
+        for op in ops:
+            impl.apply(op, e, crops[t])        # ctypes releases the GIL
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    return threads * cw * ch * len(ops), dt, kind, f"{threads} crop(s) of {cw}x{ch} x {len(ops)} op(s)"
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.workload
+    element, ops, w, h, planes, seed, desc = WORKLOADS[name]
+    threads = os.cpu_count() or 1
+    for _ in range(min(args.warmup, 1)):
+        run_reference_once(name, threads)
+    total, secs = 0, 0.0
+    for k in range(args.steps):
+        n, dt, kind, sample = run_reference_once(name, threads, seed_offset=k)
+        total += n
+        secs += dt
+    value = total / secs / 1e6
+    print(json.dumps({
+        "impl": "reference", "metric": "morsi Mpixel/s", "value": value, "unit": "Mpixel/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "element": element, "ops": ops},
+        "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": threads, "kind": kind,
+                         "sample": sample + " per step, one crop per host thread"},
+        "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------
+def main_ours(args):
+    import imscript_b200 as M
+    from imscript_b200.binding import check
+    L = M.lib()
+    world, rank, local, dist, torch = dist_setup(args.gpus)
+    if M.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; libmorsi_cuda has no CPU fallback")
+    check(L.morsi_cuda_init(local))
+    name = args.workload
+    element, ops, w, h, planes, seed, desc = WORKLOADS[name]
+    e = M.parse_element(element)
+    e_p = e.ctypes.data_as(M.binding._i32p)
+    opi = [M.OPS.index(o) for o in ops]
+    sharded = name == "c4"
+
+    if sharded:
+        from imscript_b200 import shard
+        job = shard.BandJob(L, opi[0], e, w, h, rank, world, dist, torch, seed)
+        samples_per_step_total = w * h * len(ops)
+        step = job.step
+        scaling = "strong"
+    else:
+        n = w * h * planes
+        d_x = M.DeviceBuffer(n * 4)
+        d_y = M.DeviceBuffer(n * 4)
+        for p in range(planes):
+            check(L.morsi_cuda_synth(d_x.ptr + p * w * h * 4, w, h, 0, p + rank * planes, seed, 0, None))
+        check(L.morsi_cuda_sync(None))
+        samples_per_step_total = n * len(ops) * world
+        scaling = "weak"
+
+        def step():
+            for o in opi:
+                check(L.morsi_cuda_apply_device(o, e_p, d_x.ptr, d_y.ptr, w, h, planes, None))
+
+    def barrier():
+        check(L.morsi_cuda_sync(None))
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+
+    ev = [M.binding._vp() for _ in range(2)]
+    for x in ev:
+        check(L.morsi_cuda_event_create(M.binding.ctypes.byref(x)))
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    L.morsi_cuda_launch_count_reset()
+    check(L.morsi_cuda_event_record(ev[0], None))
+    for _ in range(args.steps):
+        step()
+    check(L.morsi_cuda_event_record(ev[1], None))
+    check(L.morsi_cuda_sync(None))
+    launches = L.morsi_cuda_launch_count()
+    ms = M.binding.ctypes.c_float()
+    check(L.morsi_cuda_event_elapsed_ms(ev[0], ev[1], M.binding.ctypes.byref(ms)))
+    barrier()
+    clocks = sampler.stop()
+    elapsed_ms = ms.value
+    if dist is not None:
+        t = torch.tensor([elapsed_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = samples_per_step_total / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: the public host-pointer call, pinned host buffers ----------
+    e2e = None
+    if not sharded:
+        hx, hy = M.binding._vp(), M.binding._vp()
+        nbytes = w * h * planes * 4
+        check(L.morsi_cuda_host_alloc(M.binding.ctypes.byref(hx), nbytes))
+        check(L.morsi_cuda_host_alloc(M.binding.ctypes.byref(hy), nbytes))
+        check(L.morsi_cuda_memcpy_d2h(hx, d_x.ptr, nbytes, None))
+        check(L.morsi_cuda_sync(None))
+        e2e_steps = max(1, min(args.steps, 5))
+
+        def e2e_step():
+            for o in opi:
+                check(L.morsi_cuda_apply(o, e_p, hx, hy, w, h, planes))
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": samples_per_step_total * e2e_steps / dt / 1e6, "unit": "Mpixel/s",
+               "h2d_bytes_per_step": nbytes * len(ops), "d2h_bytes_per_step": nbytes * len(ops),
+               "steps": e2e_steps, "api": "morsi_cuda_apply (host pointers, pinned)"}
+        L.morsi_cuda_host_free(hx)
+        L.morsi_cuda_host_free(hy)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel family ---------------------------
+    peak, peak_src = peaks()
+    per_gpu_samples_per_op = samples_per_step_total / world / len(ops)
+    op_ms = ms_per_step / len(ops)
+    achieved = 8.0 * per_gpu_samples_per_op / (op_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_sample": 8,
+                "note": "per-operation duration = step time / ops per step (CUDA events on the launching stream)"}
+    tr = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tr):
+        try:
+            roofline["traffic"] = json.load(open(tr)).get(name)
+        except Exception:
+            pass
+
+    # ---- CPU baseline: the reference on ONE host thread, bounded sample ----
+    cpu = None
+    if not args.no_cpu:
+        n, dt, kind, sample = run_reference_once(name, 1, big=True)
+        cpu = {"value": n / dt / 1e6, "unit": "Mpixel/s", "cores": 1, "kind": kind,
+               "sample": sample + f", {dt:.1f} s"}
+
+    print(json.dumps({
+        "metric": "morsi Mpixel/s", "value": value, "unit": "Mpixel/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": desc, "element": element, "ops": ops, "samples_per_step": samples_per_step_total,
+                   "l2": "input+output per op exceed the 126 MB L2" if w * h * planes * 8 > 126e6
+                   else "working set fits L2 (launch-latency-bound config)"},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+    }))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        main_reference(args)
+    else:
+        main_ours(args)
+
+
+if __name__ == "__main__":
+    main()
