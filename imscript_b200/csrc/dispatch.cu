@@ -43,17 +43,27 @@ void morsi_element_compile(MorsiCtx *, DevElement *d)
 	}
 }
 
-static dim3 exact_grid(int w, int rows, int planes)
+// Gated launches (re-runs that are no-ops unless a -0.0 was seen) use a small
+// grid-stride grid so that the usual no-op costs a few microseconds.
+static dim3 exact_grid(int w, int rows, int planes, bool gated)
 {
+	unsigned gx = (unsigned)((w + 31) / 32);
 	unsigned gy = (unsigned)((rows + 7) / 8);
 	if (gy > 16384) gy = 16384;
-	return dim3((unsigned)((w + 31) / 32), gy, (unsigned)planes);
+	if (gated) {
+		unsigned long long cap = 148ull * 16;
+		unsigned long long per_row = (unsigned long long)gx * (unsigned)planes;
+		unsigned want = (unsigned)(cap / (per_row ? per_row : 1));
+		if (want < 1) want = 1;
+		if (gy > want) gy = want;
+	}
+	return dim3(gx, gy, (unsigned)planes);
 }
 
 template <int EPI>
 static void launch_exact_t(const ExactArgs &a, int planes, cudaStream_t s)
 {
-	k_exact_minmax<EPI><<<exact_grid(a.w, a.y_rows, planes), dim3(32, 8), 0, s>>>(a);
+	k_exact_minmax<EPI><<<exact_grid(a.w, a.y_rows, planes, a.gate != nullptr), dim3(32, 8), 0, s>>>(a);
 	morsi_count_launch(1);
 }
 
@@ -85,7 +95,7 @@ int morsi_run_exact(MorsiCtx *c, const DevElement *de, const MorsiJob &job, cons
 		m.x_src = xb; m.y = job.y; m.y_pstride = job.y_pstride;
 		m.y_row0 = job.y_row0; m.y_rows = job.y_rows; m.w = w; m.h = h;
 		m.offs = de->d_offs; m.n = de->n; m.gate = gate;
-		dim3 g = exact_grid(w, job.y_rows, job.planes);
+		dim3 g = exact_grid(w, job.y_rows, job.planes, gate != nullptr);
 		if (plan.special == 1) k_exact_median<<<g, dim3(32, 8), 0, job.stream>>>(m);
 		else k_exact_rank<<<g, dim3(32, 8), 0, job.stream>>>(m);
 		morsi_count_launch(1);
@@ -127,29 +137,59 @@ int morsi_run_exact(MorsiCtx *c, const DevElement *de, const MorsiJob &job, cons
 	return launch_exact(plan.epi, a, job.planes, job.stream);
 }
 
+// Exact path with bounded temporaries: the job is cut into plane groups and
+// row chunks so that a two-stage temporary never exceeds ~256 MiB per slot.
+static int run_exact_chunked(MorsiCtx *c, const DevElement *de, const MorsiJob &job, const int *gate)
+{
+	const OpPlan plan = morsi_op_plan(job.op);
+	const long long budget = 256LL << 20;
+	const int halo = plan.stages == 2 ? (de->info.ymax - de->info.ymin + 1) : 0;
+	long long row_bytes = (long long)job.w * 4;
+	long long rows_fit = budget / row_bytes - halo;
+	if (rows_fit < 16) rows_fit = 16;
+	int planes_per = 1, rows_per = job.y_rows;
+	if (plan.stages != 2) {
+		planes_per = job.planes;                       // no temporaries at all
+	} else if (rows_fit >= job.y_rows) {
+		long long pp = budget / (row_bytes * (job.y_rows + halo));
+		planes_per = (int)(pp < 1 ? 1 : pp > job.planes ? job.planes : pp);
+	} else {
+		rows_per = (int)rows_fit;
+	}
+	for (int p0 = 0; p0 < job.planes; p0 += planes_per)
+		for (int r0 = 0; r0 < job.y_rows; r0 += rows_per) {
+			MorsiJob sub = job;
+			sub.planes = job.planes - p0 < planes_per ? job.planes - p0 : planes_per;
+			sub.x = job.x + p0 * job.x_pstride;
+			sub.y = job.y + p0 * job.y_pstride + (long long)r0 * job.w;
+			sub.y_row0 = job.y_row0 + r0;
+			sub.y_rows = job.y_rows - r0 < rows_per ? job.y_rows - r0 : rows_per;
+			int rc = morsi_run_exact(c, de, sub, gate);
+			if (rc) return rc;
+		}
+	return MORSI_OK;
+}
+
 int morsi_dispatch(MorsiCtx *c, const int *e, const MorsiJob &job)
 {
 	const DevElement *de = nullptr;
 	int rc = morsi_element_get(c, e, &de);
 	if (rc) return rc;
-	// temporaries of two-stage exact passes are sized by the plane batch: keep
-	// them below 2 GiB per slot by splitting the batch
-	const OpPlan plan = morsi_op_plan(job.op);
-	if (plan.stages == 2 && job.planes > 1) {
-		long long per_plane = (long long)job.w * (job.y_rows + 2LL * (de->info.ymax - de->info.ymin + 1)) * 4;
-		long long max_planes = (2LL << 30) / (per_plane > 0 ? per_plane : 1);
-		if (max_planes < 1) max_planes = 1;
-		if (job.planes > max_planes) {
-			for (int p0 = 0; p0 < job.planes; p0 += (int)max_planes) {
-				MorsiJob sub = job;
-				sub.planes = job.planes - p0 < max_planes ? job.planes - p0 : (int)max_planes;
-				sub.x = job.x + p0 * job.x_pstride;
-				sub.y = job.y + p0 * job.y_pstride;
-				rc = morsi_dispatch(c, e, sub);
-				if (rc) return rc;
-			}
-			return MORSI_OK;
-		}
+	const int path = morsi_path();
+	if (path != 1) {
+		// fast families reorder the reduction; they raise *flag when the data
+		// holds a -0.0, and the order-preserving kernels (no-ops while the
+		// flag is clear) then redo the job
+		int *flag = c->d_flag + job.lane;
+		MORSI_CU(cudaMemsetAsync(flag, 0, sizeof(int), job.stream));
+		int handled = 0;
+		rc = morsi_run_small(c, de, job, flag, &handled);
+		if (rc) return rc;
+		if (!handled) { rc = morsi_run_march(c, de, job, flag, &handled); if (rc) return rc; }
+		if (!handled) { rc = morsi_run_median(c, de, job, flag, &handled); if (rc) return rc; }
+		if (!handled) { rc = morsi_run_tiled(c, de, job, flag, &handled); if (rc) return rc; }
+		if (handled)
+			return path == 2 ? MORSI_OK : run_exact_chunked(c, de, job, flag);
 	}
-	return morsi_run_exact(c, de, job, nullptr);
+	return run_exact_chunked(c, de, job, nullptr);
 }

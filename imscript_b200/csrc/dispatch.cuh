@@ -69,6 +69,11 @@ int morsi_ws_get(MorsiCtx *c, int lane, int slot, size_t bytes, void **out);
 int morsi_element_get(MorsiCtx *c, const int *e, const DevElement **out);
 void morsi_element_compile(MorsiCtx *c, DevElement *d);
 int morsi_dispatch(MorsiCtx *c, const int *e, const MorsiJob &job);
+// fast kernel families: set *handled = 1 when they took the job
+int morsi_run_small(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
+int morsi_run_march(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
+int morsi_run_median(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
+int morsi_run_tiled(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 
 #define MORSI_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
 	return morsi_set_error(e_ == cudaErrorMemoryAllocation ? MORSI_ERR_OOM : MORSI_ERR_CUDA, \

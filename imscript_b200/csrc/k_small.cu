@@ -1,0 +1,309 @@
+// k_small.cu -- HBM-bound kernels for structuring elements inside the 3x3
+// neighbourhood (cross, square, disk2, hrec2, vrec2, ...): BASELINE configs
+// C1 (square erosion) and C5 (cross gradient).
+//
+// No shared memory: every thread owns 4 adjacent columns (one float4 load and
+// one float4 store per row, fully coalesced), gets the neighbouring columns
+// from the adjacent lanes with warp shuffles, and marches down its rows with a
+// 3-row window in registers.  Two-stage operations (opening, closing, tophat,
+// bothat, oscillation) keep the intermediate erosion/dilation rows in
+// registers too, so every operation moves 4 B in + 4 B out per sample.
+// Reductions use min.f32/max.f32 (FMNMX/FMNMX3), which ignore NaN operands
+// exactly like fmin/fmax; they are not order-preserving for +0/-0, so any -0.0
+// seen in the loaded data raises *flag and the dispatcher re-runs the
+// order-preserving kernels.
+#include "dispatch.cuh"
+
+struct SmallArgs {
+	Band x;
+	float *y;
+	long long y_pstride;
+	int y_row0, y_rows;
+	int w, h;
+	unsigned mask;      // bit (dy+1)*3+(dx+1)
+	int rows_per_warp;
+	int epi;            // Epi
+	int stage1_min, stage1_max;   // two-stage: which temporaries exist
+	int need_a, need_b;           // final pass: erosion side / dilation side
+	int a_from_tmax, b_from_tmin; // two-stage: A = min over tmax, B = max over tmin
+	int *flag;
+};
+
+template <bool ISMAX> __device__ __forceinline__ float mm(float a, float b)
+{
+	return ISMAX ? fmaxf(a, b) : fminf(a, b);
+}
+
+// reduction over the masked 3x3 neighbourhood of column c (window columns
+// c..c+2 of the three rows)
+template <int MASK, bool ISMAX, int N>
+__device__ __forceinline__ float red3x3(const float (&up)[N], const float (&mid)[N],
+		const float (&dn)[N], int c, unsigned rmask)
+{
+	float r = ISMAX ? -CUDART_INF_F : CUDART_INF_F;
+	const unsigned m = MASK >= 0 ? (unsigned)MASK : rmask;
+#pragma unroll
+	for (int dx = 0; dx < 3; dx++) {
+		if (m & (1u << dx))       r = mm<ISMAX>(r, up[c + dx]);
+		if (m & (1u << (3 + dx))) r = mm<ISMAX>(r, mid[c + dx]);
+		if (m & (1u << (6 + dx))) r = mm<ISMAX>(r, dn[c + dx]);
+	}
+	return r;
+}
+
+__device__ __forceinline__ float apply_epi(int epi, float a, float b, float x)
+{
+	switch (epi) {
+	case EPI_A: return a;
+	case EPI_B: return b;
+	case EPI_B_SUB_A: return epilogue<EPI_B_SUB_A>(a, b, x);
+	case EPI_X_SUB_A: return epilogue<EPI_X_SUB_A>(a, b, x);
+	case EPI_B_SUB_X: return epilogue<EPI_B_SUB_X>(a, b, x);
+	case EPI_LAP: return epilogue<EPI_LAP>(a, b, x);
+	case EPI_ENH: return epilogue<EPI_ENH>(a, b, x);
+	case EPI_BLUR: return epilogue<EPI_BLUR>(a, b, x);
+	case EPI_A_SUB_B: return epilogue<EPI_A_SUB_B>(a, b, x);
+	case EPI_X_SUB_B: return epilogue<EPI_X_SUB_B>(a, b, x);
+	case EPI_A_SUB_X: return epilogue<EPI_A_SUB_X>(a, b, x);
+	case EPI_IBLUR: return epilogue<EPI_IBLUR>(a, b, x);
+	case EPI_EBLUR: return epilogue<EPI_EBLUR>(a, b, x);
+	case EPI_CBLUR: return epilogue<EPI_CBLUR>(a, b, x);
+	}
+	return a;
+}
+
+// Load input row j, columns x0-HALO .. x0+3+HALO, into v[0 .. 4+2*HALO).
+// Out-of-image samples are NaN.  VEC: rows are 16-byte aligned and w % 4 == 0.
+template <int HALO, bool VEC>
+__device__ __forceinline__ void load_row(const float *plane, int row0, int w, int h,
+		int j, int x0, int lane, float (&v)[4 + 2 * HALO], unsigned &negzero)
+{
+	const float nan = CUDART_NAN_F;
+	float c0 = nan, c1 = nan, c2 = nan, c3 = nan;
+	const bool row_ok = j >= 0 && j < h;
+	const float *row = plane + (long long)(j - row0) * w;
+	if (row_ok) {
+		if (VEC) {
+			if (x0 < w) {
+				float4 q = __ldg(reinterpret_cast<const float4 *>(row + x0));
+				c0 = q.x; c1 = q.y; c2 = q.z; c3 = q.w;
+			}
+		} else {
+			if (x0 < w) c0 = __ldg(row + x0);
+			if (x0 + 1 < w) c1 = __ldg(row + x0 + 1);
+			if (x0 + 2 < w) c2 = __ldg(row + x0 + 2);
+			if (x0 + 3 < w) c3 = __ldg(row + x0 + 3);
+		}
+	}
+	negzero |= (__float_as_uint(c0) == 0x80000000u) | (__float_as_uint(c1) == 0x80000000u) |
+	           (__float_as_uint(c2) == 0x80000000u) | (__float_as_uint(c3) == 0x80000000u);
+	v[HALO] = c0; v[HALO + 1] = c1; v[HALO + 2] = c2; v[HALO + 3] = c3;
+	// neighbours from the adjacent lanes
+	float l1 = __shfl_up_sync(0xffffffffu, c3, 1);
+	float r1 = __shfl_down_sync(0xffffffffu, c0, 1);
+	float l2 = nan, r2 = nan;
+	if (HALO == 2) {
+		l2 = __shfl_up_sync(0xffffffffu, c2, 1);
+		r2 = __shfl_down_sync(0xffffffffu, c1, 1);
+	}
+	if (lane == 0) {
+		l1 = (row_ok && x0 - 1 >= 0 && x0 - 1 < w) ? __ldg(row + x0 - 1) : nan;
+		if (HALO == 2) l2 = (row_ok && x0 - 2 >= 0 && x0 - 2 < w) ? __ldg(row + x0 - 2) : nan;
+		negzero |= (__float_as_uint(l1) == 0x80000000u) | (__float_as_uint(l2) == 0x80000000u);
+	}
+	if (lane == 31) {
+		r1 = (row_ok && x0 + 4 < w) ? __ldg(row + x0 + 4) : nan;
+		if (HALO == 2) r2 = (row_ok && x0 + 5 < w) ? __ldg(row + x0 + 5) : nan;
+		negzero |= (__float_as_uint(r1) == 0x80000000u) | (__float_as_uint(r2) == 0x80000000u);
+	}
+	if (HALO == 1) { v[0] = l1; v[5] = r1; }
+	else { v[0] = l2; v[1] = l1; v[6] = r1; v[7] = r2; }
+}
+
+template <bool VEC>
+__device__ __forceinline__ void store_row(float *yrow, int x0, int w, const float (&o)[4])
+{
+	if (VEC) {
+		if (x0 < w) *reinterpret_cast<float4 *>(yrow + x0) = make_float4(o[0], o[1], o[2], o[3]);
+	} else {
+#pragma unroll
+		for (int c = 0; c < 4; c++)
+			if (x0 + c < w) yrow[x0 + c] = o[c];
+	}
+}
+
+// ---- single stage -----------------------------------------------------------
+template <int MASK, bool VEC>
+__global__ void __launch_bounds__(256) k_small_1(SmallArgs p)
+{
+	const int lane = threadIdx.x;
+	const int x0 = (blockIdx.x * 32 + lane) * 4;
+	const int plane = blockIdx.z;
+	const int seg = blockIdx.y * blockDim.y + threadIdx.y;
+	const int jj0 = seg * p.rows_per_warp;
+	if (jj0 >= p.y_rows) return;
+	const int jj1 = min(p.y_rows, jj0 + p.rows_per_warp);
+	const int y0 = p.y_row0 + jj0, y1 = p.y_row0 + jj1;
+	const float *xp = p.x.p + plane * p.x.pstride;
+	float *yp = p.y + plane * p.y_pstride;
+	unsigned negzero = 0;
+
+	float in[3][6];
+	// input rows j = y0-1 .. y1 ; slot of row j is (j-(y0-1)) % 3
+	load_row<1, VEC>(xp, p.x.row0, p.w, p.h, y0 - 1, x0, lane, in[0], negzero);
+	load_row<1, VEC>(xp, p.x.row0, p.w, p.h, y0, x0, lane, in[1], negzero);
+	for (int jb = y0 + 1; jb <= y1; jb += 3) {
+#pragma unroll
+		for (int u = 0; u < 3; u++) {
+			const int j = jb + u;               // slot (u+2)%3
+			if (j <= y1) {
+				load_row<1, VEC>(xp, p.x.row0, p.w, p.h, j, x0, lane, in[(u + 2) % 3], negzero);
+				const float (&up)[6] = in[u % 3];
+				const float (&mid)[6] = in[(u + 1) % 3];
+				const float (&dn)[6] = in[(u + 2) % 3];
+				float o[4];
+#pragma unroll
+				for (int c = 0; c < 4; c++) {
+					float a = 0.f, b = 0.f;
+					if (p.need_a) a = red3x3<MASK, false>(up, mid, dn, c, p.mask);
+					if (p.need_b) b = red3x3<MASK, true>(up, mid, dn, c, p.mask);
+					o[c] = apply_epi(p.epi, a, b, mid[c + 1]);
+				}
+				store_row<VEC>(yp + (long long)(j - 1 - p.y_row0) * p.w, x0, p.w, o);
+			}
+		}
+	}
+	if (__any_sync(0xffffffffu, negzero) && lane == 0) atomicOr(p.flag, 1);
+}
+
+// ---- two stages fused ---------------------------------------------------------
+template <int MASK, bool VEC, bool OSC>
+__global__ void __launch_bounds__(256) k_small_2(SmallArgs p)
+{
+	const int lane = threadIdx.x;
+	const int x0 = (blockIdx.x * 32 + lane) * 4;
+	const int plane = blockIdx.z;
+	const int seg = blockIdx.y * blockDim.y + threadIdx.y;
+	const int jj0 = seg * p.rows_per_warp;
+	if (jj0 >= p.y_rows) return;
+	const int jj1 = min(p.y_rows, jj0 + p.rows_per_warp);
+	const int y0 = p.y_row0 + jj0, y1 = p.y_row0 + jj1;
+	const float *xp = p.x.p + plane * p.x.pstride;
+	float *yp = p.y + plane * p.y_pstride;
+	unsigned negzero = 0;
+	const float nan = CUDART_NAN_F;
+
+	float in[3][8];     // input rows, columns x0-2 .. x0+5
+	float t1[3][6];     // first temporary rows, columns x0-1 .. x0+4
+	float t2[3][6];     // second temporary (oscillation only)
+	// column validity of the temporaries (outside the image they are absent)
+	bool cok[6];
+#pragma unroll
+	for (int c = 0; c < 6; c++) cok[c] = (x0 - 1 + c >= 0) && (x0 - 1 + c < p.w);
+
+	// input rows j = y0-2 .. y1+1, slot (j-(y0-2)) % 3
+	// temporary row t = j-1 becomes available after loading row j; slot (t-(y0-1)) % 3
+	// output row t-1 = j-2 after temporary rows j-3, j-2, j-1 exist
+	load_row<2, VEC>(xp, p.x.row0, p.w, p.h, y0 - 2, x0, lane, in[0], negzero);
+	load_row<2, VEC>(xp, p.x.row0, p.w, p.h, y0 - 1, x0, lane, in[1], negzero);
+	for (int jb = y0; jb <= y1 + 1; jb += 3) {
+#pragma unroll
+		for (int u = 0; u < 3; u++) {
+			const int j = jb + u;
+			if (j <= y1 + 1) {
+				load_row<2, VEC>(xp, p.x.row0, p.w, p.h, j, x0, lane, in[(u + 2) % 3], negzero);
+				const float (&iu)[8] = in[u % 3];
+				const float (&im)[8] = in[(u + 1) % 3];
+				const float (&id)[8] = in[(u + 2) % 3];
+				// temporary row t = j-1 -> slot u
+				const int t = j - 1;
+				const bool trow = t >= 0 && t < p.h;
+#pragma unroll
+				for (int c = 0; c < 6; c++) {
+					float v1, v2 = nan;
+					if (OSC) {
+						v1 = red3x3<MASK, false>(iu, im, id, c, p.mask);
+						v2 = red3x3<MASK, true>(iu, im, id, c, p.mask);
+					} else {
+						v1 = p.stage1_max ? red3x3<MASK, true>(iu, im, id, c, p.mask)
+						                  : red3x3<MASK, false>(iu, im, id, c, p.mask);
+					}
+					const bool ok = trow && cok[c];
+					t1[u][c] = ok ? v1 : nan;
+					if (OSC) t2[u][c] = ok ? v2 : nan;
+				}
+				if (j >= y0 + 2) {
+					// output row j-2 from temporary rows j-3 (slot u+1), j-2 (slot u+2), j-1 (slot u)
+					const float (&tu)[6] = t1[(u + 1) % 3];
+					const float (&tm)[6] = t1[(u + 2) % 3];
+					const float (&td)[6] = t1[u % 3];
+					float o[4];
+#pragma unroll
+					for (int c = 0; c < 4; c++) {
+						float a = 0.f, b = 0.f;
+						if (OSC) {
+							// closing - opening: A = min over dilation, B = max over erosion
+							a = red3x3<MASK, false>(t2[(u + 1) % 3], t2[(u + 2) % 3], t2[u % 3], c, p.mask);
+							b = red3x3<MASK, true>(tu, tm, td, c, p.mask);
+						} else if (p.stage1_max) {
+							a = red3x3<MASK, false>(tu, tm, td, c, p.mask);
+						} else {
+							b = red3x3<MASK, true>(tu, tm, td, c, p.mask);
+						}
+						// x at row j-2: input slot of row j-2 is u % 3, columns offset by 2
+						o[c] = apply_epi(p.epi, a, b, iu[c + 2]);
+					}
+					store_row<VEC>(yp + (long long)(j - 2 - p.y_row0) * p.w, x0, p.w, o);
+				}
+			}
+		}
+	}
+	if (__any_sync(0xffffffffu, negzero) && lane == 0) atomicOr(p.flag, 1);
+}
+
+// ---- host side ------------------------------------------------------------------
+template <int MASK, bool VEC>
+static void launch_small_t(const SmallArgs &a, int stages, bool osc, dim3 grid, dim3 block, cudaStream_t s)
+{
+	if (stages == 1) k_small_1<MASK, VEC><<<grid, block, 0, s>>>(a);
+	else if (osc) k_small_2<MASK, VEC, true><<<grid, block, 0, s>>>(a);
+	else k_small_2<MASK, VEC, false><<<grid, block, 0, s>>>(a);
+}
+
+// returns MORSI_OK and *handled = 1 when it launched the job
+int morsi_run_small(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled)
+{
+	*handled = 0;
+	const OpPlan plan = morsi_op_plan(job.op);
+	if (plan.special || de->info.kind != MORSI_EK_SMALL || de->n == 0) return MORSI_OK;
+	SmallArgs a;
+	a.x = Band{job.x, job.x_row0, job.x_pstride};
+	a.y = job.y; a.y_pstride = job.y_pstride; a.y_row0 = job.y_row0; a.y_rows = job.y_rows;
+	a.w = job.w; a.h = job.h; a.mask = de->info.mask3x3; a.epi = plan.epi; a.flag = flag;
+	a.stage1_min = plan.t_min; a.stage1_max = plan.t_max;
+	a.need_a = plan.a_from != 0; a.need_b = plan.b_from != 0;
+	a.a_from_tmax = plan.a_from == 3; a.b_from_tmin = plan.b_from == 2;
+	const bool osc = plan.t_min && plan.t_max;
+	const bool vec = (job.w % 4 == 0) && (((uintptr_t)job.x) % 16 == 0) && (((uintptr_t)job.y) % 16 == 0)
+		&& (job.x_pstride % 4 == 0) && (job.y_pstride % 4 == 0);
+	// rows per warp: long marches amortise the warm-up rows, but keep >= ~4 CTAs per SM
+	const int gx = (job.w + 127) / 128;
+	int rpw = 64;
+	while (rpw > 8 && (long long)gx * ((job.y_rows + rpw * 8 - 1) / (rpw * 8)) * job.planes < 4LL * c->sm_count)
+		rpw /= 2;
+	a.rows_per_warp = rpw;
+	dim3 block(32, 8);
+	dim3 grid(gx, (job.y_rows + rpw * 8 - 1) / (rpw * 8), job.planes);
+	const unsigned CROSS = 0272u /* .#. ### .#. */, SQUARE = 0777u;
+	if (vec) {
+		if (a.mask == CROSS) launch_small_t<(int)0272, true>(a, plan.stages, osc, grid, block, job.stream);
+		else if (a.mask == SQUARE) launch_small_t<(int)0777, true>(a, plan.stages, osc, grid, block, job.stream);
+		else launch_small_t<-1, true>(a, plan.stages, osc, grid, block, job.stream);
+	} else {
+		launch_small_t<-1, false>(a, plan.stages, osc, grid, block, job.stream);
+	}
+	morsi_count_launch(1);
+	MORSI_CU(cudaGetLastError());
+	*handled = 1;
+	return MORSI_OK;
+}
