@@ -195,12 +195,14 @@ def main_ours(args):
     opi = [M.OPS.index(o) for o in ops]
     sharded = name == "c4"
 
+    stream = None
     if sharded:
         from imscript_b200 import shard
         job = shard.BandJob(L, opi[0], e, w, h, rank, world, dist, torch, seed)
         samples_per_step_total = w * h * len(ops)
         step = job.step
         scaling = "strong"
+        stream = job.stream
     else:
         n = w * h * planes
         d_x = M.DeviceBuffer(n * 4)
@@ -216,7 +218,7 @@ def main_ours(args):
                 check(L.morsi_cuda_apply_device(o, e_p, d_x.ptr, d_y.ptr, w, h, planes, None))
 
     def barrier():
-        check(L.morsi_cuda_sync(None))
+        check(L.morsi_cuda_sync(stream))
         if dist is not None:
             torch.cuda.synchronize()
             dist.barrier()
@@ -231,11 +233,11 @@ def main_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     L.morsi_cuda_launch_count_reset()
-    check(L.morsi_cuda_event_record(ev[0], None))
+    check(L.morsi_cuda_event_record(ev[0], stream))
     for _ in range(args.steps):
         step()
-    check(L.morsi_cuda_event_record(ev[1], None))
-    check(L.morsi_cuda_sync(None))
+    check(L.morsi_cuda_event_record(ev[1], stream))
+    check(L.morsi_cuda_sync(stream))
     launches = L.morsi_cuda_launch_count()
     ms = M.binding.ctypes.c_float()
     check(L.morsi_cuda_event_elapsed_ms(ev[0], ev[1], M.binding.ctypes.byref(ms)))

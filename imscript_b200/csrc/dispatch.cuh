@@ -9,7 +9,7 @@
 #include "common.cuh"
 #include "element.h"
 
-#define MORSI_WS_SLOTS 4
+#define MORSI_WS_SLOTS 6   // 0-3: kernel temporaries, 4-5: host-pipeline staging
 #define MORSI_LANES 4   // lane 0: the *_device entry points; 1..3: host-pointer pipeline
 
 // compiled form of a row-run element (k_rowrun.cu)

@@ -33,9 +33,9 @@ static int run_chunks(int device, int op, const int *e, const float *x, float *y
 	float *d_in[3], *d_out[3];
 	for (int l = 0; l < lanes; l++) {
 		void *p;
-		if ((rc = morsi_ws_get(c, 1 + l, 2, max_in, &p))) return rc;
+		if ((rc = morsi_ws_get(c, 1 + l, 4, max_in, &p))) return rc;
 		d_in[l] = (float *)p;
-		if ((rc = morsi_ws_get(c, 1 + l, 3, max_out, &p))) return rc;
+		if ((rc = morsi_ws_get(c, 1 + l, 5, max_out, &p))) return rc;
 		d_out[l] = (float *)p;
 	}
 	for (size_t t = 0; t < chunks.size(); t++) {

@@ -253,18 +253,21 @@ __global__ void __launch_bounds__(128) k_march(MarchArgs p)
 					const int k1 = S::hw(1 - d > 2 * R ? 2 * R : 1 - d); // hw(dy1 + R)
 #pragma unroll
 					for (int c = 0; c < C; c++) {
-						if (d == 1) acc[c][slot] = H1[k1][c];
+						if (d == 1) acc[c][slot] = H1[k1][c];                       // first row of output i0+1
+						else if (d == 0) acc[c][slot] = ext2<ISMAX>(H0[k0][c], H1[k1][c]);   // first two rows of output i0
 						else if (d == -2 * R) acc[c][slot] = ext2<ISMAX>(acc[c][slot], H0[k0][c]);
 						else acc[c][slot] = ext3<ISMAX>(acc[c][slot], H0[k0][c], H1[k1][c]);
 					}
 				}
 				// outputs o = i0-2R and i0-2R+1 are complete
 				{
+					// folding in the start value turns an all-NaN window into +-INF,
+					// as the reference's a = +-INFINITY start does (src/morsi.c:63,77)
 					float m0[C], m1[C];
 #pragma unroll
 					for (int c = 0; c < C; c++) {
-						m0[c] = acc[c][((2 * s - 2 * R) % NACC + NACC) % NACC];
-						m1[c] = acc[c][((2 * s - 2 * R + 1) % NACC + NACC) % NACC];
+						m0[c] = ext2<ISMAX>(acc[c][((2 * s - 2 * R) % NACC + NACC) % NACC], init);
+						m1[c] = ext2<ISMAX>(acc[c][((2 * s - 2 * R + 1) % NACC + NACC) % NACC], init);
 					}
 					emit(2 * g - 2 * R, m0);
 					emit(2 * g - 2 * R + 1, m1);

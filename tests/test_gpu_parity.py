@@ -75,6 +75,23 @@ def test_vs_oracle_shapes_elements_ops(dist):
                 assert_same(M.apply(op, e, x), o.apply(op, e, x), f"{name} {op} {w}x{h} dist={dist}")
 
 
+def test_all_nan_windows_and_constant_images():
+    """windows with no usable neighbour give +-INF (src/morsi.c:63,77), also on the fast paths"""
+    o = oracle()
+    x = M.synth_host(64, 64, seed=21, dist=0)
+    x[10:50, 8:56] = np.nan
+    x[55:, :] = np.inf
+    x[:, 60:] = -np.inf
+    for name in ["cross", "square", "disk5", "disk7", "dysk4"]:
+        e = o.element(name)
+        for op in OPS:
+            assert_same(M.apply(op, e, x), o.apply(op, e, x), f"nan block {name} {op}")
+    z = np.zeros((40, 64), np.float32)
+    for name in ["square", "disk7"]:
+        for op in OPS:
+            assert_same(M.apply(op, o.element(name), z), o.apply(op, o.element(name), z), f"zeros {name} {op}")
+
+
 def test_multi_plane_and_user_lists():
     o = oracle()
     x = np.stack([M.synth_host(50, 40, plane=p, seed=4, dist=2 if p == 1 else 0) for p in range(3)])
