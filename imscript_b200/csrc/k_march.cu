@@ -25,6 +25,8 @@
 // min.f32/max.f32 do not keep the reference's last-wins order for +0/-0:
 // the kernel raises *flag when it sees a -0.0 and the dispatcher re-runs the
 // order-preserving path.
+#include <cstdlib>
+
 #include "dispatch.cuh"
 
 struct MarchArgs {
@@ -185,7 +187,7 @@ struct Marcher {
 	// They touch outputs o = i0 + d, d in [-2R, 1]; the accumulator slot of o
 	// is (2s + d) mod NACC.  Outputs i0-2R and i0-2R+1 are complete afterwards
 	// and handed to emit(which, m).
-	template <bool CHECK0, class Emit>
+	template <bool CHECK0, bool FOLD, class Emit>
 	__device__ static __forceinline__ void step(float (&acc)[C][NACC], const int s, const float *rowA, const float *rowB, bool &negzero, Emit &&emit)
 	{
 		float H0[RX + 1][C], H1[RX + 1][C];
@@ -205,14 +207,17 @@ struct Marcher {
 				else acc[c][slot] = ext3<ISMAX>(acc[c][slot], H0[k0][c], H1[k1][c]);
 			}
 		}
-		// folding in the start value turns an all-NaN window into +-INF, as the
-		// reference's a = +-INFINITY start does (src/morsi.c:63,77)
+		// FOLD: folding in the start value turns an all-NaN window into +-INF, as
+		// the reference's a = +-INFINITY start does (src/morsi.c:63,77).  The
+		// second stage of a fused pair never sees such a window (the element
+		// holds its centre and first-stage results inside the image are not NaN).
 		const float init = ISMAX ? -CUDART_INF_F : CUDART_INF_F;
 		float m0[C], m1[C];
 #pragma unroll
 		for (int c = 0; c < C; c++) {
-			m0[c] = ext2<ISMAX>(acc[c][((2 * s - 2 * R) % NACC + NACC) % NACC], init);
-			m1[c] = ext2<ISMAX>(acc[c][((2 * s - 2 * R + 1) % NACC + NACC) % NACC], init);
+			m0[c] = acc[c][((2 * s - 2 * R) % NACC + NACC) % NACC];
+			m1[c] = acc[c][((2 * s - 2 * R + 1) % NACC + NACC) % NACC];
+			if (FOLD) { m0[c] = ext2<ISMAX>(m0[c], init); m1[c] = ext2<ISMAX>(m1[c], init); }
 		}
 		emit(0, m0);
 		emit(1, m1);
@@ -312,6 +317,7 @@ __global__ void __launch_bounds__(128) k_march(MarchArgs p)
 		cp_async_commit();
 	}
 	const float *my = ring + C * tid;
+	long long yoff = -2LL * R * w;                    // element offset of output row 2g-2R
 #pragma unroll 1
 	for (int g0 = 0; g0 < G; g0 += R + 1) {
 #pragma unroll
@@ -324,14 +330,15 @@ __global__ void __launch_bounds__(128) k_march(MarchArgs p)
 				cp_async_commit();
 				const float *rowA = my + ((2 * g) & (K::NRING - 1)) * PITCH;
 				const int o0 = 2 * g - 2 * R;
-				M::template step<true>(acc, s, rowA, rowA + PITCH, negzero, [&](int which, const float (&m)[C]) {
+				M::template step<true, true>(acc, s, rowA, rowA + PITCH, negzero, [&](int which, const float (&m)[C]) {
 					const int o = o0 + which;
 					if (o < 0 || o >= nout || !col_ok) return;
-					float *q = yq + (long long)o * w;
-					if (plain) { store_cols<C>(q, m); return; }
-					march_emit_general<ISMAX>(q, xq ? xq + (long long)o * w : nullptr, oq ? oq + (long long)o * w : nullptr,
+					const long long off = which ? yoff + w : yoff;
+					if (plain) { store_cols<C>(yq + off, m); return; }
+					march_emit_general<ISMAX>(yq + off, xq ? xq + off : nullptr, oq ? oq + off : nullptr,
 							epi, C, m[0], m[1], C == 4 ? m[2] : 0.f, C == 4 ? m[3] : 0.f);
 				});
+				yoff += 2 * w;
 			}
 		}
 	}
@@ -396,6 +403,7 @@ __global__ void __launch_bounds__(256) k_march2(MarchArgs p)
 	}
 	const float *my_in = ring + C * mt;
 	const float *my_t = tring + C * mt;
+	long long yoff = -2LL * R * w;                    // element offset of output row 2*g2-2R (second stage)
 #pragma unroll 1
 	for (int g0 = 0; g0 < GT; g0 += R + 1) {
 #pragma unroll
@@ -411,7 +419,7 @@ __global__ void __launch_bounds__(256) k_march2(MarchArgs p)
 						const float *rowA = my_in + ((2 * g) & (K::NRING - 1)) * PITCH;
 						// temporary rows completed by this step: index 2(g-R), 2(g-R)+1 from global row Y0-R
 						const int tp = g - R;
-						M1::template step<true>(acc, s, rowA, rowA + PITCH, negzero, [&](int which, const float (&m)[C]) {
+						M1::template step<true, true>(acc, s, rowA, rowA + PITCH, negzero, [&](int which, const float (&m)[C]) {
 							if (tp < 0) return;
 							const int tr = Y0 - R + 2 * tp + which;          // global row of the temporary
 							float *q = tring + ((2 * tp + which) & (K::NTRING - 1)) * PITCHT + C * mt;
@@ -429,14 +437,15 @@ __global__ void __launch_bounds__(256) k_march2(MarchArgs p)
 					if (g2 >= 0) {
 						const float *rowA = my_t + ((2 * g2) & (K::NTRING - 1)) * PITCHT;
 						const int o0 = 2 * g2 - 2 * R;
-						M2::template step<false>(acc, s, rowA, rowA + PITCHT, negzero, [&](int which, const float (&m)[C]) {
+						M2::template step<false, false>(acc, s, rowA, rowA + PITCHT, negzero, [&](int which, const float (&m)[C]) {
 							const int o = o0 + which;
 							if (o < 0 || o >= nout || !col_ok) return;
-							float *q = yq + (long long)o * w;
-							if (plain) { store_cols<C>(q, m); return; }
-							march_emit_general<!S1MAX>(q, xq ? xq + (long long)o * w : nullptr, nullptr,
+							const long long off = which ? yoff + w : yoff;
+							if (plain) { store_cols<C>(yq + off, m); return; }
+							march_emit_general<!S1MAX>(yq + off, xq ? xq + off : nullptr, nullptr,
 									epi, C, m[0], m[1], C == 4 ? m[2] : 0.f, C == 4 ? m[3] : 0.f);
 						});
+						yoff += 2 * w;
 					}
 				}
 			}
@@ -447,18 +456,26 @@ __global__ void __launch_bounds__(256) k_march2(MarchArgs p)
 }
 
 // ---- host side --------------------------------------------------------------------
-// Bands: one wave of CTAs when the job allows it (no tail), never shorter than
-// 16 reaches (march warm-up <= 12 %), even row counts.
+// Bands: every CTA marches `rows` output rows plus a warm-up of 2*reach rows
+// per stage, and CTAs run in waves of `slots`; pick the band count that
+// minimises waves x (rows + warm-up), i.e. no half-empty last wave.
 static int pick_band_rows(const MorsiCtx *c, int y_rows, long long strips_x_planes, int ctas_per_sm, int reach, int stages)
 {
-	long long slots = (long long)c->sm_count * ctas_per_sm;
-	long long bands = slots / (strips_x_planes > 0 ? strips_x_planes : 1);
-	if (bands < 1) bands = 1;
-	long long rows = (y_rows + bands - 1) / bands;
-	const long long min_rows = 16LL * reach * stages > 64 ? 16LL * reach * stages : 64;
-	if (rows < min_rows) rows = min_rows;
-	if (rows > y_rows) rows = y_rows;
-	return (int)((rows + 1) & ~1LL);
+	const long long slots = (long long)c->sm_count * ctas_per_sm;
+	const int warm = 2 * reach * stages + 12;          // rows of warm-up + fixed per-CTA cost
+	const int min_rows = 8 * reach * stages > 32 ? 8 * reach * stages : 32;
+	int best_rows = y_rows;
+	double best = 1e300;
+	for (int bands = 1; bands <= 4096; bands++) {
+		int rows = (y_rows + bands - 1) / bands;
+		rows = (rows + 1) & ~1;
+		if (rows < min_rows && bands > 1) break;
+		const long long ctas = strips_x_planes * ((y_rows + rows - 1) / rows);
+		const long long waves = (ctas + slots - 1) / slots;
+		const double cost = (double)waves * (rows + warm);
+		if (cost < best * 0.999) { best = cost; best_rows = rows; }
+	}
+	return best_rows;
 }
 
 template <class S, int C, bool ISMAX>
@@ -509,6 +526,9 @@ template <int ID>
 static int launch_shape2(MorsiCtx *c, const MarchArgs &a, int planes, bool s1max, cudaStream_t st)
 {
 	constexpr int C = Shape<ID>::R <= 8 ? 4 : 2;
+	if (ID == 13 && getenv("MORSI_MARCH_C4"))
+		return s1max ? launch_march2<Shape<13>, 4, true>(c, a, planes, st)
+		             : launch_march2<Shape<13>, 4, false>(c, a, planes, st);
 	return s1max ? launch_march2<Shape<ID>, C, true>(c, a, planes, st)
 	             : launch_march2<Shape<ID>, C, false>(c, a, planes, st);
 }
