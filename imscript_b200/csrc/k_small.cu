@@ -72,53 +72,75 @@ __device__ __forceinline__ float apply_epi(int epi, float a, float b, float x)
 	return a;
 }
 
-// Load input row j, columns x0-HALO .. x0+3+HALO, into v[0 .. 4+2*HALO).
-// Out-of-image samples are NaN.  VEC: rows are 16-byte aligned and w % 4 == 0.
+// One input row as fetched from global memory: this thread's 4 columns plus,
+// on the warp's edge lanes, the columns just outside the warp's span.  Fetching
+// is split from assembling so that the loads of a row PF rows ahead are in
+// flight while the current row is reduced (one float4 per thread per row is far
+// too little memory-level parallelism to fill HBM otherwise).
+template <int HALO>
+struct RawRow {
+	float c[4];
+	float e[HALO];      // lane 0: columns x0-1 (, x0-2); lane 31: columns x0+4 (, x0+5)
+};
+
 template <int HALO, bool VEC>
-__device__ __forceinline__ void load_row(const float *plane, int row0, int w, int h,
-		int j, int x0, int lane, float (&v)[4 + 2 * HALO], unsigned &negzero)
+__device__ __forceinline__ void fetch_row(const float *plane, int row0, int w, int h,
+		int j, int x0, int lane, RawRow<HALO> &r)
 {
 	const float nan = CUDART_NAN_F;
-	float c0 = nan, c1 = nan, c2 = nan, c3 = nan;
-	const bool row_ok = j >= 0 && j < h;
+#pragma unroll
+	for (int k = 0; k < 4; k++) r.c[k] = nan;
+#pragma unroll
+	for (int k = 0; k < HALO; k++) r.e[k] = nan;
+	if (j < 0 || j >= h) return;
 	const float *row = plane + (long long)(j - row0) * w;
-	if (row_ok) {
-		if (VEC) {
-			if (x0 < w) {
-				float4 q = __ldg(reinterpret_cast<const float4 *>(row + x0));
-				c0 = q.x; c1 = q.y; c2 = q.z; c3 = q.w;
-			}
-		} else {
-			if (x0 < w) c0 = __ldg(row + x0);
-			if (x0 + 1 < w) c1 = __ldg(row + x0 + 1);
-			if (x0 + 2 < w) c2 = __ldg(row + x0 + 2);
-			if (x0 + 3 < w) c3 = __ldg(row + x0 + 3);
+	if (VEC) {
+		if (x0 < w) {
+			float4 q = __ldg(reinterpret_cast<const float4 *>(row + x0));
+			r.c[0] = q.x; r.c[1] = q.y; r.c[2] = q.z; r.c[3] = q.w;
 		}
-	}
-	negzero |= (__float_as_uint(c0) == 0x80000000u) | (__float_as_uint(c1) == 0x80000000u) |
-	           (__float_as_uint(c2) == 0x80000000u) | (__float_as_uint(c3) == 0x80000000u);
-	v[HALO] = c0; v[HALO + 1] = c1; v[HALO + 2] = c2; v[HALO + 3] = c3;
-	// neighbours from the adjacent lanes
-	float l1 = __shfl_up_sync(0xffffffffu, c3, 1);
-	float r1 = __shfl_down_sync(0xffffffffu, c0, 1);
-	float l2 = nan, r2 = nan;
-	if (HALO == 2) {
-		l2 = __shfl_up_sync(0xffffffffu, c2, 1);
-		r2 = __shfl_down_sync(0xffffffffu, c1, 1);
+	} else {
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			if (x0 + k < w) r.c[k] = __ldg(row + x0 + k);
 	}
 	if (lane == 0) {
-		l1 = (row_ok && x0 - 1 >= 0 && x0 - 1 < w) ? __ldg(row + x0 - 1) : nan;
-		if (HALO == 2) l2 = (row_ok && x0 - 2 >= 0 && x0 - 2 < w) ? __ldg(row + x0 - 2) : nan;
-		negzero |= (__float_as_uint(l1) == 0x80000000u) | (__float_as_uint(l2) == 0x80000000u);
+#pragma unroll
+		for (int k = 0; k < HALO; k++)
+			if (x0 - 1 - k >= 0 && x0 - 1 - k < w) r.e[k] = __ldg(row + x0 - 1 - k);
 	}
 	if (lane == 31) {
-		r1 = (row_ok && x0 + 4 < w) ? __ldg(row + x0 + 4) : nan;
-		if (HALO == 2) r2 = (row_ok && x0 + 5 < w) ? __ldg(row + x0 + 5) : nan;
-		negzero |= (__float_as_uint(r1) == 0x80000000u) | (__float_as_uint(r2) == 0x80000000u);
+#pragma unroll
+		for (int k = 0; k < HALO; k++)
+			if (x0 + 4 + k < w) r.e[k] = __ldg(row + x0 + 4 + k);
 	}
+}
+
+// columns x0-HALO .. x0+3+HALO of a fetched row into v[0 .. 4+2*HALO)
+template <int HALO>
+__device__ __forceinline__ void assemble_row(const RawRow<HALO> &r, int lane,
+		float (&v)[4 + 2 * HALO], unsigned &negzero)
+{
+	negzero |= (__float_as_uint(r.c[0]) == 0x80000000u) | (__float_as_uint(r.c[1]) == 0x80000000u) |
+	           (__float_as_uint(r.c[2]) == 0x80000000u) | (__float_as_uint(r.c[3]) == 0x80000000u);
+#pragma unroll
+	for (int k = 0; k < HALO; k++) negzero |= (__float_as_uint(r.e[k]) == 0x80000000u);
+#pragma unroll
+	for (int k = 0; k < 4; k++) v[HALO + k] = r.c[k];
+	float l1 = __shfl_up_sync(0xffffffffu, r.c[3], 1);
+	float r1 = __shfl_down_sync(0xffffffffu, r.c[0], 1);
+	float l2 = 0.f, r2 = 0.f;
+	if (HALO == 2) {
+		l2 = __shfl_up_sync(0xffffffffu, r.c[2], 1);
+		r2 = __shfl_down_sync(0xffffffffu, r.c[1], 1);
+	}
+	if (lane == 0) { l1 = r.e[0]; if (HALO == 2) l2 = r.e[HALO - 1]; }
+	if (lane == 31) { r1 = r.e[0]; if (HALO == 2) r2 = r.e[HALO - 1]; }
 	if (HALO == 1) { v[0] = l1; v[5] = r1; }
 	else { v[0] = l2; v[1] = l1; v[6] = r1; v[7] = r2; }
 }
+
+#define SMALL_PF 3     // rows fetched ahead of the row being reduced
 
 template <bool VEC>
 __device__ __forceinline__ void store_row(float *yrow, int x0, int w, const float (&o)[4])
@@ -149,15 +171,25 @@ __global__ void __launch_bounds__(256) k_small_1(SmallArgs p)
 	unsigned negzero = 0;
 
 	float in[3][6];
-	// input rows j = y0-1 .. y1 ; slot of row j is (j-(y0-1)) % 3
-	load_row<1, VEC>(xp, p.x.row0, p.w, p.h, y0 - 1, x0, lane, in[0], negzero);
-	load_row<1, VEC>(xp, p.x.row0, p.w, p.h, y0, x0, lane, in[1], negzero);
+	RawRow<1> raw[SMALL_PF];
+	// input rows j = y0-1 .. y1 ; window slot of row j is (j-(y0-1)) % 3 and its
+	// prefetch slot the same (SMALL_PF == 3); rows are fetched SMALL_PF ahead
+#pragma unroll
+	for (int k = 0; k < SMALL_PF; k++)
+		fetch_row<1, VEC>(xp, p.x.row0, p.w, p.h, y0 - 1 + k, x0, lane, raw[k]);
+	assemble_row<1>(raw[0], lane, in[0], negzero);
+	// (never fetch below row y1: the source band may end there)
+	if (y0 - 1 + SMALL_PF <= y1) fetch_row<1, VEC>(xp, p.x.row0, p.w, p.h, y0 - 1 + SMALL_PF, x0, lane, raw[0]);
+	assemble_row<1>(raw[1], lane, in[1], negzero);
+	if (y0 + SMALL_PF <= y1) fetch_row<1, VEC>(xp, p.x.row0, p.w, p.h, y0 + SMALL_PF, x0, lane, raw[1]);
 	for (int jb = y0 + 1; jb <= y1; jb += 3) {
 #pragma unroll
 		for (int u = 0; u < 3; u++) {
 			const int j = jb + u;               // slot (u+2)%3
 			if (j <= y1) {
-				load_row<1, VEC>(xp, p.x.row0, p.w, p.h, j, x0, lane, in[(u + 2) % 3], negzero);
+				assemble_row<1>(raw[(u + 2) % 3], lane, in[(u + 2) % 3], negzero);
+				if (j + SMALL_PF <= y1)
+					fetch_row<1, VEC>(xp, p.x.row0, p.w, p.h, j + SMALL_PF, x0, lane, raw[(u + 2) % 3]);
 				const float (&up)[6] = in[u % 3];
 				const float (&mid)[6] = in[(u + 1) % 3];
 				const float (&dn)[6] = in[(u + 2) % 3];
@@ -204,14 +236,22 @@ __global__ void __launch_bounds__(256) k_small_2(SmallArgs p)
 	// input rows j = y0-2 .. y1+1, slot (j-(y0-2)) % 3
 	// temporary row t = j-1 becomes available after loading row j; slot (t-(y0-1)) % 3
 	// output row t-1 = j-2 after temporary rows j-3, j-2, j-1 exist
-	load_row<2, VEC>(xp, p.x.row0, p.w, p.h, y0 - 2, x0, lane, in[0], negzero);
-	load_row<2, VEC>(xp, p.x.row0, p.w, p.h, y0 - 1, x0, lane, in[1], negzero);
+	RawRow<2> raw[SMALL_PF];
+#pragma unroll
+	for (int k = 0; k < SMALL_PF; k++)
+		fetch_row<2, VEC>(xp, p.x.row0, p.w, p.h, y0 - 2 + k, x0, lane, raw[k]);
+	assemble_row<2>(raw[0], lane, in[0], negzero);
+	fetch_row<2, VEC>(xp, p.x.row0, p.w, p.h, y0 - 2 + SMALL_PF, x0, lane, raw[0]);
+	assemble_row<2>(raw[1], lane, in[1], negzero);
+	fetch_row<2, VEC>(xp, p.x.row0, p.w, p.h, y0 - 1 + SMALL_PF, x0, lane, raw[1]);
 	for (int jb = y0; jb <= y1 + 1; jb += 3) {
 #pragma unroll
 		for (int u = 0; u < 3; u++) {
 			const int j = jb + u;
 			if (j <= y1 + 1) {
-				load_row<2, VEC>(xp, p.x.row0, p.w, p.h, j, x0, lane, in[(u + 2) % 3], negzero);
+				assemble_row<2>(raw[(u + 2) % 3], lane, in[(u + 2) % 3], negzero);
+				if (j + SMALL_PF <= y1 + 1)
+					fetch_row<2, VEC>(xp, p.x.row0, p.w, p.h, j + SMALL_PF, x0, lane, raw[(u + 2) % 3]);
 				const float (&iu)[8] = in[u % 3];
 				const float (&im)[8] = in[(u + 1) % 3];
 				const float (&id)[8] = in[(u + 2) % 3];
