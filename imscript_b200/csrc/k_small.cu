@@ -155,7 +155,44 @@ __device__ __forceinline__ void store_row(float *yrow, int x0, int w, const floa
 }
 
 // ---- single stage -----------------------------------------------------------
-template <int MASK, bool VEC>
+// Branch-free row fetch for the single-stage kernel: one predicated float4
+// load per lane plus one predicated scalar load on the two edge lanes of the
+// warp (lane 0: column x0-1, lane 31: column x0+4).
+struct Raw1 { float4 q; float e; };
+
+template <bool VEC>
+__device__ __forceinline__ void fetch1(const float *row, bool row_ok, bool col_ok, bool edge_ok, int eoff,
+		int w, int x0, Raw1 &r)
+{
+	const float nan = CUDART_NAN_F;
+	r.q = make_float4(nan, nan, nan, nan);
+	r.e = nan;
+	if (VEC) {
+		if (row_ok && col_ok) r.q = __ldg(reinterpret_cast<const float4 *>(row));
+	} else {
+		if (row_ok && x0 < w) r.q.x = __ldg(row);
+		if (row_ok && x0 + 1 < w) r.q.y = __ldg(row + 1);
+		if (row_ok && x0 + 2 < w) r.q.z = __ldg(row + 2);
+		if (row_ok && x0 + 3 < w) r.q.w = __ldg(row + 3);
+	}
+	if (row_ok && edge_ok) r.e = __ldg(row + eoff);
+}
+
+__device__ __forceinline__ void assemble1(const Raw1 &r, int lane, float (&v)[6], unsigned &negzero)
+{
+	negzero |= (__float_as_uint(r.q.x) == 0x80000000u) | (__float_as_uint(r.q.y) == 0x80000000u) |
+	           (__float_as_uint(r.q.z) == 0x80000000u) | (__float_as_uint(r.q.w) == 0x80000000u) |
+	           (__float_as_uint(r.e) == 0x80000000u);
+	const float l1 = __shfl_up_sync(0xffffffffu, r.q.w, 1);
+	const float r1 = __shfl_down_sync(0xffffffffu, r.q.x, 1);
+	v[0] = lane == 0 ? r.e : l1;
+	v[1] = r.q.x; v[2] = r.q.y; v[3] = r.q.z; v[4] = r.q.w;
+	v[5] = lane == 31 ? r.e : r1;
+}
+
+// EPI >= 0: the epilogue (and with it which of min / max is needed) is a
+// compile-time constant; EPI < 0: taken from p.epi at run time.
+template <int MASK, bool VEC, int EPI>
 __global__ void __launch_bounds__(256) k_small_1(SmallArgs p)
 {
 	const int lane = threadIdx.x;
@@ -166,30 +203,46 @@ __global__ void __launch_bounds__(256) k_small_1(SmallArgs p)
 	if (jj0 >= p.y_rows) return;
 	const int jj1 = min(p.y_rows, jj0 + p.rows_per_warp);
 	const int y0 = p.y_row0 + jj0, y1 = p.y_row0 + jj1;
-	const float *xp = p.x.p + plane * p.x.pstride;
-	float *yp = p.y + plane * p.y_pstride;
+	const int w = p.w, h = p.h;
 	unsigned negzero = 0;
+	constexpr bool CT = EPI >= 0;
+	const bool need_a = CT ? EpiNeeds<CT ? EPI : 0>::a : (p.need_a != 0);
+	const bool need_b = CT ? EpiNeeds<CT ? EPI : 0>::b : (p.need_b != 0);
+
+	// running pointers: next row to fetch, next row to store
+	const float *fp = p.x.p + plane * p.x.pstride + (long long)(y0 - 1 - p.x.row0) * w + x0;
+	int fj = y0 - 1;                                  // global row fp points at
+	float *yq = p.y + plane * p.y_pstride + (long long)(y0 - p.y_row0) * w + x0;
+
+	// loop-invariant predicates of the fetch
+	const bool col_ok = x0 < w;
+	const int eoff = lane == 0 ? -1 : 4;
+	const bool edge_ok = (lane == 0 && x0 > 0 && x0 - 1 < w) || (lane == 31 && x0 + 4 < w);
 
 	float in[3][6];
-	RawRow<1> raw[SMALL_PF];
+	Raw1 raw[SMALL_PF];
 	// input rows j = y0-1 .. y1 ; window slot of row j is (j-(y0-1)) % 3 and its
-	// prefetch slot the same (SMALL_PF == 3); rows are fetched SMALL_PF ahead
+	// prefetch slot the same (SMALL_PF == 3); rows are fetched SMALL_PF ahead,
+	// never below row y1 (the source band may end there)
 #pragma unroll
-	for (int k = 0; k < SMALL_PF; k++)
-		fetch_row<1, VEC>(xp, p.x.row0, p.w, p.h, y0 - 1 + k, x0, lane, raw[k]);
-	assemble_row<1>(raw[0], lane, in[0], negzero);
-	// (never fetch below row y1: the source band may end there)
-	if (y0 - 1 + SMALL_PF <= y1) fetch_row<1, VEC>(xp, p.x.row0, p.w, p.h, y0 - 1 + SMALL_PF, x0, lane, raw[0]);
-	assemble_row<1>(raw[1], lane, in[1], negzero);
-	if (y0 + SMALL_PF <= y1) fetch_row<1, VEC>(xp, p.x.row0, p.w, p.h, y0 + SMALL_PF, x0, lane, raw[1]);
+	for (int k = 0; k < SMALL_PF; k++) {
+		fetch1<VEC>(fp, (unsigned)fj < (unsigned)h && fj <= y1, col_ok, edge_ok, eoff, w, x0, raw[k]);
+		fp += w; fj++;
+	}
+	assemble1(raw[0], lane, in[0], negzero);
+	fetch1<VEC>(fp, (unsigned)fj < (unsigned)h && fj <= y1, col_ok, edge_ok, eoff, w, x0, raw[0]);
+	fp += w; fj++;
+	assemble1(raw[1], lane, in[1], negzero);
+	fetch1<VEC>(fp, (unsigned)fj < (unsigned)h && fj <= y1, col_ok, edge_ok, eoff, w, x0, raw[1]);
+	fp += w; fj++;
 	for (int jb = y0 + 1; jb <= y1; jb += 3) {
 #pragma unroll
 		for (int u = 0; u < 3; u++) {
 			const int j = jb + u;               // slot (u+2)%3
 			if (j <= y1) {
-				assemble_row<1>(raw[(u + 2) % 3], lane, in[(u + 2) % 3], negzero);
-				if (j + SMALL_PF <= y1)
-					fetch_row<1, VEC>(xp, p.x.row0, p.w, p.h, j + SMALL_PF, x0, lane, raw[(u + 2) % 3]);
+				assemble1(raw[(u + 2) % 3], lane, in[(u + 2) % 3], negzero);
+				fetch1<VEC>(fp, (unsigned)fj < (unsigned)h && fj <= y1, col_ok, edge_ok, eoff, w, x0, raw[(u + 2) % 3]);
+				fp += w; fj++;
 				const float (&up)[6] = in[u % 3];
 				const float (&mid)[6] = in[(u + 1) % 3];
 				const float (&dn)[6] = in[(u + 2) % 3];
@@ -197,11 +250,13 @@ __global__ void __launch_bounds__(256) k_small_1(SmallArgs p)
 #pragma unroll
 				for (int c = 0; c < 4; c++) {
 					float a = 0.f, b = 0.f;
-					if (p.need_a) a = red3x3<MASK, false>(up, mid, dn, c, p.mask);
-					if (p.need_b) b = red3x3<MASK, true>(up, mid, dn, c, p.mask);
-					o[c] = apply_epi(p.epi, a, b, mid[c + 1]);
+					if (need_a) a = red3x3<MASK, false>(up, mid, dn, c, p.mask);
+					if (need_b) b = red3x3<MASK, true>(up, mid, dn, c, p.mask);
+					o[c] = CT ? epilogue<CT ? EPI : 0>(a, b, mid[c + 1]) : apply_epi(p.epi, a, b, mid[c + 1]);
 				}
-				store_row<VEC>(yp + (long long)(j - 1 - p.y_row0) * p.w, x0, p.w, o);
+				if (VEC) { if (col_ok) *reinterpret_cast<float4 *>(yq) = make_float4(o[0], o[1], o[2], o[3]); }
+				else store_row<VEC>(yq - x0, x0, w, o);
+				yq += w;
 			}
 		}
 	}
@@ -305,7 +360,17 @@ __global__ void __launch_bounds__(256) k_small_2(SmallArgs p)
 template <int MASK, bool VEC>
 static void launch_small_t(const SmallArgs &a, int stages, bool osc, dim3 grid, dim3 block, cudaStream_t s)
 {
-	if (stages == 1) k_small_1<MASK, VEC><<<grid, block, 0, s>>>(a);
+	if (stages == 1) {
+		if (VEC) {
+			switch (a.epi) {
+#define E(X) case X: k_small_1<MASK, VEC, X><<<grid, block, 0, s>>>(a); return;
+			E(EPI_A) E(EPI_B) E(EPI_B_SUB_A) E(EPI_X_SUB_A) E(EPI_B_SUB_X) E(EPI_LAP) E(EPI_ENH) E(EPI_BLUR)
+			E(EPI_IBLUR) E(EPI_EBLUR) E(EPI_CBLUR)
+#undef E
+			}
+		}
+		k_small_1<MASK, VEC, -1><<<grid, block, 0, s>>>(a);
+	}
 	else if (osc) k_small_2<MASK, VEC, true><<<grid, block, 0, s>>>(a);
 	else k_small_2<MASK, VEC, false><<<grid, block, 0, s>>>(a);
 }
