@@ -6,7 +6,7 @@ NVCC   ?= nvcc
 CC     ?= gcc
 REF    ?= /root/reference
 ARCH   := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v $(EXTRA)
 SRC    := imscript_b200/csrc
 OUT    := imscript_b200/lib
 OBJ    := build/obj

@@ -3,6 +3,7 @@
 // composite wrappers of src/morsi.c:141-275,509-543.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "dispatch.cuh"
 #include "k_exact.cuh"
@@ -185,9 +186,15 @@ int morsi_dispatch(MorsiCtx *c, const int *e, const MorsiJob &job)
 		int handled = 0;
 		rc = morsi_run_small(c, de, job, flag, &handled);
 		if (rc) return rc;
-		if (!handled) { rc = morsi_run_march(c, de, job, flag, &handled); if (rc) return rc; }
-		if (!handled) { rc = morsi_run_median(c, de, job, flag, &handled); if (rc) return rc; }
-		if (!handled) { rc = morsi_run_tiled(c, de, job, flag, &handled); if (rc) return rc; }
+		static const bool old_march = getenv("MORSI_DISK") && !strcmp(getenv("MORSI_DISK"), "0");
+		if (!handled && !old_march) { rc = morsi_run_disk(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 2; }
+		if (!handled) { rc = morsi_run_march(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 3; }
+		if (!handled) { rc = morsi_run_median(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 4; }
+		if (!handled) { rc = morsi_run_tiled(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 5; }
+		if (getenv("MORSI_CUDA_TRACE"))
+			fprintf(stderr, "morsi_cuda: op %d n=%d %dx%dx%d rows [%d,+%d): %s\n", job.op, de->n, job.w, job.h, job.planes,
+				job.y_row0, job.y_rows, handled == 1 ? "small" : handled == 2 ? "disk" : handled == 3 ? "march (old)" :
+				handled == 4 ? "median" : handled == 5 ? "tiled" : "exact only");
 		if (handled)
 			return path == 2 ? MORSI_OK : run_exact_chunked(c, de, job, flag);
 	}

@@ -71,6 +71,7 @@ void morsi_element_compile(MorsiCtx *c, DevElement *d);
 int morsi_dispatch(MorsiCtx *c, const int *e, const MorsiJob &job);
 // fast kernel families: set *handled = 1 when they took the job
 int morsi_run_small(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
+int morsi_run_disk(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_march(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_median(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_tiled(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);

@@ -1,0 +1,822 @@
+// k_disk.cu -- erosion / dilation by convex symmetric "row-run" elements
+// (disks): BASELINE configs C2 (disk7 opening/closing) and C4 (disk15 tophat).
+//
+// A disk of reach R is one centred run per row, half-width hw(dy).  The kernel
+// is a streaming register march over a column strip and a row band:
+//   * the strip's input rows (plus halo columns) stream through a shared-memory
+//     ring of row GROUPS.  One elected lane issues one TMA tensor copy
+//     (cp.async.bulk.tensor.4d -> UTMALDG) per group, a group ahead of the
+//     compute; completion is signalled on an mbarrier per ring slot, the
+//     consumer warps hand the slot back through a second mbarrier -- one barrier
+//     round trip per group, not per row.  The tensor map views a plane as
+//     (bw, w/bw, rows, planes) so that a box row of any width is one dense
+//     shared-memory row, and fills everything outside the image with NaN
+//     (CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA), which min.f32 /
+//     max.f32 ignore -- exactly the reference's getpixel_nan border rule
+//     (src/morsi.c:30-35), done by the copy engine;
+//   * a thread owns C adjacent columns and walks down the band two rows at a
+//     time.  For each new row it builds the nested horizontal running extrema
+//     H_k(x) = ext(in[x-k..x+k]) with one 3-input FMNMX3 per k, and folds
+//     H_{hw(dy)} of the row pair into the 2R+2 register accumulators of the
+//     output rows the pair touches (one FMNMX3 per accumulator and pair).  The
+//     2M+1 centre rows of a disk share one half-width, so their contribution is
+//     folded once from pair / quad / octet extrema that all outputs share.
+//     Cost per sample and stage: about RX + (R - M) + 2.5 FMNMX instead of the
+//     n = e[0] fmin/fmax calls of src/morsi.c:65 (12 vs 145 for disk7, 26.5 vs
+//     697 for disk15);
+//   * two-stage operations (opening, closing, tophat, bothat) run both stages
+//     in one CTA: the first half of the warps reduces the input ring into a
+//     small shared-memory ring of temporary rows, the second half reduces that
+//     ring and writes the result -- the temporary image of src/morsi.c:143-146
+//     never exists in HBM (4 B read + 4 B written per sample).  The first
+//     stage stores its rows NEGATED: max(t) = -min(-t), so both halves run the
+//     same instruction stream (one copy in the instruction cache).  Temporary
+//     samples outside the image are NaN (absent), SURVEY.md 9.1-B.
+// The accumulator ring is addressed at compile time by unrolling R+1 steps, so
+// the element's shape is a template parameter (shapes.cuh).
+//
+// min.f32/max.f32 do not keep the reference's last-wins order for +0/-0:
+// the kernel raises *flag when it sees a -0.0 and the dispatcher re-runs the
+// order-preserving path.
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+
+#include <cuda.h>
+
+#include "dispatch.cuh"
+#include "shapes.cuh"
+
+struct DiskArgs {
+	Band src;          // image the (first) reduction runs over
+	Band xop;          // x operand of the epilogue (may be unused)
+	Band other;        // second reduction operand of the epilogue (single stage only)
+	float *y;
+	long long y_pstride;
+	int y_row0, y_rows;
+	int src_rows;      // rows held by src (for the loader's bounds)
+	int w, h;
+	int band_rows;     // output rows per CTA
+	int epi;
+	int *flag;
+};
+
+// ---- small PTX wrappers ------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx(unsigned bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		"WAIT_%=:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@!p bra WAIT_%=;\n"
+		"}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+// Wait executed by a whole (converged) warp.  The lanes of a warp can leave the
+// try_wait loop in different iterations; nothing would reconverge them
+// afterwards, and the lanes that fell behind would keep reading ring slots
+// that lane 0 -- which arrives for the warp -- has already handed back.
+__device__ __forceinline__ void mbar_wait_warp(unsigned bar, unsigned parity)
+{
+	mbar_wait(bar, parity);
+	__syncwarp();
+}
+// one group of rows of the strip, global -> shared, by the TMA engine; completion on `bar`
+__device__ __forceinline__ void tma_load_4d(unsigned dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, unsigned bar)
+{
+	asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+		:: "r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+
+template <bool ISMAX> __device__ __forceinline__ float dext2(float a, float b)
+{
+	return ISMAX ? fmaxf(a, b) : fminf(a, b);
+}
+template <bool ISMAX> __device__ __forceinline__ float dext3(float a, float b, float c)
+{
+	return ISMAX ? fmaxf(fmaxf(a, b), c) : fminf(fminf(a, b), c);   // one FMNMX3
+}
+
+__device__ __forceinline__ float disk_epi(int epi, float a, float b, float x)
+{
+	switch (epi) {
+	case EPI_A: return a;
+	case EPI_B: return b;
+	case EPI_B_SUB_A: return epilogue<EPI_B_SUB_A>(a, b, x);
+	case EPI_X_SUB_A: return epilogue<EPI_X_SUB_A>(a, b, x);
+	case EPI_B_SUB_X: return epilogue<EPI_B_SUB_X>(a, b, x);
+	case EPI_LAP: return epilogue<EPI_LAP>(a, b, x);
+	case EPI_ENH: return epilogue<EPI_ENH>(a, b, x);
+	case EPI_BLUR: return epilogue<EPI_BLUR>(a, b, x);
+	case EPI_A_SUB_B: return epilogue<EPI_A_SUB_B>(a, b, x);
+	case EPI_X_SUB_B: return epilogue<EPI_X_SUB_B>(a, b, x);
+	case EPI_A_SUB_X: return epilogue<EPI_A_SUB_X>(a, b, x);
+	case EPI_IBLUR: return epilogue<EPI_IBLUR>(a, b, x);
+	case EPI_EBLUR: return epilogue<EPI_EBLUR>(a, b, x);
+	case EPI_CBLUR: return epilogue<EPI_CBLUR>(a, b, x);
+	}
+	return a;
+}
+
+// Epilogue with extra operands (single-stage kernel), kept out of line: the
+// unrolled march calls it from 2(R+1) places.
+template <bool ISMAX>
+__device__ __noinline__ void disk_emit_general(float *q, const float *qx, const float *qo, int epi, int ncol,
+		float m0, float m1, float m2, float m3)
+{
+	float m[4] = {m0, m1, m2, m3};
+	float xv[4] = {0.f, 0.f, 0.f, 0.f}, ov[4] = {0.f, 0.f, 0.f, 0.f}, out[4];
+	if (qx) {
+		if (ncol == 4) { float4 t = __ldg((const float4 *)qx); xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w; }
+		else { float2 t = __ldg((const float2 *)qx); xv[0] = t.x; xv[1] = t.y; }
+	}
+	if (qo) {
+		if (ncol == 4) { float4 t = __ldg((const float4 *)qo); ov[0] = t.x; ov[1] = t.y; ov[2] = t.z; ov[3] = t.w; }
+		else { float2 t = __ldg((const float2 *)qo); ov[0] = t.x; ov[1] = t.y; }
+	}
+#pragma unroll
+	for (int c = 0; c < 4; c++)
+		out[c] = ISMAX ? disk_epi(epi, ov[c], m[c], xv[c]) : disk_epi(epi, m[c], ov[c], xv[c]);
+	if (ncol == 4) *(float4 *)q = make_float4(out[0], out[1], out[2], out[3]);
+	else *(float2 *)q = make_float2(out[0], out[1]);
+}
+
+// ---- compile-time geometry ---------------------------------------------------------
+template <class S> struct DiskShape {
+	static constexpr int R = S::R;
+	static constexpr int RX = S::hw(R);               // half-width of the centre row
+	// the centre run: rows R-M .. R+M all have half-width RX
+	__host__ __device__ static constexpr int centre()
+	{
+		int m = 0;
+		while (m < R && S::hw(R - m - 1) == RX && S::hw(R + m + 1) == RX) m++;
+		return m;
+	}
+	static constexpr int M = centre();
+	// pair/quad/octet sharing pays from 3 full centre pairs on
+	static constexpr bool SHARE = M >= 3 && M <= 5 && M < R;
+};
+
+template <class S, int C, int W, bool TWO>
+struct DiskCfg {
+	static constexpr int R = S::R;
+	static constexpr int RX = DiskShape<S>::RX;
+	// A thread's window starts LH columns left of its own columns; two stages
+	// need an even LH (their windows nest with 16-byte alignment).
+	static constexpr int LH = TWO ? (RX + 1) / 2 * 2 : (RX + 3) / 4 * 4;
+	static constexpr int NV = (C + LH + RX + C - 1) / C * C;    // floats a thread reads per row
+	static constexpr int NT = 32 * W;                 // threads per stage
+	static constexpr int TW = NT * C;                 // columns a stage produces per row
+	static constexpr int OUTW = TWO ? (TW - LH - RX) / 4 * 4 : TW;   // output columns per strip
+	// ring row: the windows of all threads (TW + NV - C floats) plus the slack
+	// that lets the TMA box start on a bw <= 32 column boundary; whole 128 bytes
+	static constexpr int RP = (TW + NV - C + 28 + 31) / 32 * 32;
+	// The march is unrolled over PERIOD steps (a multiple of R+1, the period of
+	// the accumulator ring).  Rows travel in groups of GP pairs (GP divides
+	// PERIOD, so a step's place in its group is a compile-time constant).
+	static constexpr int PERIOD = (R + 1) * ((6 + R) / (R + 1));
+	__host__ __device__ static constexpr int group_pairs()
+	{
+		int best = 1;
+		for (int d = 1; d <= PERIOD; d++)
+			if (PERIOD % d == 0 && d * 2 * RP * 4 <= 18 * 1024) best = d;
+		return best;
+	}
+	static constexpr int GP = group_pairs();          // row pairs per group
+	static constexpr int NG = 2;                      // groups per ring (double buffer)
+	static constexpr int PAIR = 2 * RP;               // floats per row pair
+	static constexpr int GROUP = GP * PAIR;           // floats per group
+	static constexpr unsigned GROUP_BYTES = GROUP * 4u;
+	static constexpr int NACC = 2 * R + 2;            // accumulator slots per column
+	static constexpr int THREADS = TWO ? 2 * NT : NT;
+	static constexpr size_t SMEM = (size_t)NG * GROUP * (TWO ? 2 : 1) * sizeof(float)
+		+ 4 * NG * sizeof(unsigned long long) + 128;
+	// registers: the small disks need ~160 (3 CTAs of 128 threads per SM), the big ones all 255
+#ifndef DISK_REGS_SMALL
+#define DISK_REGS_SMALL 168
+#endif
+	static constexpr int REGS = (C * (2 * R + 2) > 64) ? 255 : DISK_REGS_SMALL;
+	static constexpr int MINB = 65536 / (REGS * THREADS) > 0 ? 65536 / (REGS * THREADS) : 1;
+};
+
+// ---- the per-thread march ------------------------------------------------------------
+template <class S, int C, int LH, bool ISMAX>
+struct DiskMarch {
+	using G = DiskShape<S>;
+	static constexpr int R = G::R, RX = G::RX, M = G::M;
+	static constexpr bool SHARE = G::SHARE;
+	static constexpr int NV = (C + LH + RX + C - 1) / C * C;
+	static constexpr int NACC = 2 * R + 2;
+
+	__device__ static __forceinline__ float init() { return ISMAX ? -CUDART_INF_F : CUDART_INF_F; }
+
+	// nested horizontal extrema of one ring row; `base` points at the window's first float
+	__device__ static __forceinline__ void chain(const float *base, float (&H)[RX + 1][C], int &zmin, bool check0)
+	{
+		float v[NV];
+#pragma unroll
+		for (int q = 0; q < NV / C; q++) {
+			if (C == 4) { float4 t = *(const float4 *)(base + 4 * q); v[4*q] = t.x; v[4*q+1] = t.y; v[4*q+2] = t.z; v[4*q+3] = t.w; }
+			else { float2 t = *(const float2 *)(base + 2 * q); v[2*q] = t.x; v[2*q+1] = t.y; }
+		}
+		// -0.0 is INT_MIN as a signed word: one 3-input integer min per two samples
+		if (check0) {
+#pragma unroll
+			for (int c = 0; c < C; c += 2)
+				zmin = min(min(zmin, __float_as_int(v[LH + c])), __float_as_int(v[LH + c + 1]));
+		}
+#pragma unroll
+		for (int c = 0; c < C; c++) {
+			H[0][c] = v[LH + c];
+#pragma unroll
+			for (int k = 1; k <= RX; k++)
+				H[k][c] = dext3<ISMAX>(H[k - 1][c], v[LH + c - k], v[LH + c + k]);
+		}
+	}
+
+	// One step = march rows i0 = 2g and i1 = 2g+1 (s = g mod (R+1); the caller's
+	// loop over s is fully unrolled, so every index below folds to a constant).
+	// They touch outputs o = i0 + d, d in [-2R, 1]; row i0 is row j0 = -d of
+	// output o's window, row i1 is row j1 = 1-d.  The accumulator slot of o is
+	// (2s + d) mod NACC.  Outputs i0-2R and i0-2R+1 are complete afterwards.
+	// hs[c][]: P1 (pair extremum of the previous step), Q1, Q2 (quads ending
+	// one / two steps ago), O1 (octet ending one step ago).
+	template <class Release, class Emit>
+	__device__ static __forceinline__ void step(float (&acc)[C][NACC], float (&hs)[C][4], const int s,
+			const float *rowA, const float *rowB, int &zmin, bool check0, Release &&release, Emit &&emit)
+	{
+		float H0[RX + 1][C], H1[RX + 1][C];
+		chain(rowA, H0, zmin, check0);
+		chain(rowB, H1, zmin, check0);
+		release();                     // the ring slot has been read
+		float P0[C], Q0[C], O0[C];
+		if (SHARE) {
+#pragma unroll
+			for (int c = 0; c < C; c++) {
+				// the start value rides along: an all-NaN window must give +-INF
+				// (src/morsi.c:63,77), and every output holds a centre pair
+				P0[c] = dext3<ISMAX>(H0[RX][c], H1[RX][c], init());
+				Q0[c] = dext2<ISMAX>(hs[c][0], P0[c]);
+				O0[c] = M == 5 ? dext2<ISMAX>(hs[c][2], Q0[c]) : 0.f;
+			}
+		}
+#pragma unroll
+		for (int d = -2 * R; d <= 1; d++) {
+			const int slot = ((2 * s + d) % NACC + NACC) % NACC;
+			const int j0 = -d, j1 = 1 - d;
+			const bool in0 = j0 >= 0, in1 = j1 <= 2 * R;
+			const int k0 = S::hw(j0 < 0 ? 0 : j0);
+			const int k1 = S::hw(j1 > 2 * R ? 2 * R : j1);
+			const bool centre_pair = SHARE && in0 && in1 && j0 >= R - M && j1 <= R + M;
+			const bool last_centre_pair = centre_pair && j1 + 2 > R + M;
+#pragma unroll
+			for (int c = 0; c < C; c++) {
+				if (centre_pair) {
+					if (last_centre_pair) {
+						if (M == 3) acc[c][slot] = dext3<ISMAX>(acc[c][slot], hs[c][1], P0[c]);
+						if (M == 4) acc[c][slot] = dext3<ISMAX>(acc[c][slot], hs[c][2], Q0[c]);
+						if (M == 5) acc[c][slot] = dext3<ISMAX>(acc[c][slot], hs[c][3], P0[c]);
+					}
+				} else if (!in0) {
+					acc[c][slot] = SHARE ? H1[k1][c] : dext2<ISMAX>(H1[k1][c], init());
+				} else if (j0 == 0) {
+					acc[c][slot] = dext3<ISMAX>(H0[k0][c], H1[k1][c], init());
+				} else if (!in1) {
+					acc[c][slot] = dext2<ISMAX>(acc[c][slot], H0[k0][c]);
+				} else {
+					acc[c][slot] = dext3<ISMAX>(acc[c][slot], H0[k0][c], H1[k1][c]);
+				}
+			}
+		}
+		if (SHARE) {
+#pragma unroll
+			for (int c = 0; c < C; c++) {
+				hs[c][3] = O0[c];
+				hs[c][2] = hs[c][1];
+				hs[c][1] = Q0[c];
+				hs[c][0] = P0[c];
+			}
+		}
+		float m0[C], m1[C];
+#pragma unroll
+		for (int c = 0; c < C; c++) {
+			m0[c] = acc[c][((2 * s - 2 * R) % NACC + NACC) % NACC];
+			m1[c] = acc[c][((2 * s - 2 * R + 1) % NACC + NACC) % NACC];
+		}
+		emit(m0, m1);
+	}
+};
+
+template <int C>
+__device__ __forceinline__ void store_cols(float *q, const float (&m)[C])
+{
+	if (C == 4) *(float4 *)q = make_float4(m[0], m[1], m[2], m[3]);
+	else *(float2 *)q = make_float2(m[0], m[1]);
+}
+template <int C>
+__device__ __forceinline__ void load_cols(const float *q, float (&m)[C])
+{
+	if (C == 4) { float4 t = __ldg((const float4 *)q); m[0] = t.x; m[1] = t.y; m[2] = t.z; m[3] = t.w; }
+	else { float2 t = __ldg((const float2 *)q); m[0] = t.x; m[1] = t.y; }
+}
+
+// first stage, rare path: a temporary row pair that touches the image border
+// (scalars by value: arrays by reference would force the caller's rows into
+// local memory on the common path too)
+__device__ __noinline__ void disk_store_tmp_masked(float *q0, float *q1, int ncol, unsigned colmask, bool row0_ok, bool row1_ok,
+		float a0, float a1, float a2, float a3, float b0, float b1, float b2, float b3)
+{
+	const float nan = CUDART_NAN_F;
+	a0 = (colmask & 1u) && row0_ok ? a0 : nan; b0 = (colmask & 1u) && row1_ok ? b0 : nan;
+	a1 = (colmask & 2u) && row0_ok ? a1 : nan; b1 = (colmask & 2u) && row1_ok ? b1 : nan;
+	a2 = (colmask & 4u) && row0_ok ? a2 : nan; b2 = (colmask & 4u) && row1_ok ? b2 : nan;
+	a3 = (colmask & 8u) && row0_ok ? a3 : nan; b3 = (colmask & 8u) && row1_ok ? b3 : nan;
+	if (ncol == 4) { *(float4 *)q0 = make_float4(a0, a1, a2, a3); *(float4 *)q1 = make_float4(b0, b1, b2, b3); }
+	else { *(float2 *)q0 = make_float2(a0, a1); *(float2 *)q1 = make_float2(b0, b1); }
+}
+
+// ---- the kernel ----------------------------------------------------------------------
+// TWO: warps [0,W) run the first reduction over the input ring, warps [W,2W)
+// the second one over the temporary ring (ISMAX is the FIRST stage's flavour,
+// and -- through the negated temporaries -- the flavour both halves compute).
+// HASX (TWO only): the epilogue subtracts: tophat x - opening (ISMAX = false),
+// bothat closing - x (ISMAX = true); src/morsi.c:229-245.
+// tm: the source band as a (bw, w/bw, rows, planes) tensor, box (bw, RP/bw, 2*GP, 1).
+template <class S, int C, int W, bool ISMAX, bool TWO, bool HASX>
+__global__ void __launch_bounds__(DiskCfg<S, C, W, TWO>::THREADS, DiskCfg<S, C, W, TWO>::MINB)
+k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
+{
+	using K = DiskCfg<S, C, W, TWO>;
+	using D = DiskMarch<S, C, K::LH, ISMAX>;
+	constexpr int R = K::R, LH = K::LH, RP = K::RP, PERIOD = K::PERIOD, GP = K::GP, NG = K::NG;
+	constexpr int PAIR = K::PAIR, GROUP = K::GROUP;
+	extern __shared__ unsigned char smem_raw[];
+	// 128-byte aligned base (TMA destination)
+	float *ring = reinterpret_cast<float *>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));   // NG groups
+	float *tring = ring + (TWO ? (size_t)NG * GROUP : 0);              // the same for the temporaries
+	const unsigned bars = smem_u32(tring + (size_t)NG * GROUP);
+	const unsigned full_in = bars, empty_in = bars + 8 * NG;
+	const unsigned full_t = bars + 16 * NG, empty_t = bars + 24 * NG;
+
+	const int tid = threadIdx.x;
+	const int lane = tid & 31;
+	const bool first = TWO && tid < K::NT;            // warp-uniform role
+	const bool reads_input = !TWO || first;
+	const int mt = TWO ? (first ? tid : tid - K::NT) : tid;
+	const int plane = blockIdx.z;
+	const int cx0 = blockIdx.x * K::OUTW;             // first output column of the strip
+	const int o_base = blockIdx.y * p.band_rows;      // first output row of the band (relative)
+	const int nout = min(p.band_rows, p.y_rows - o_base);
+	const int Y0 = p.y_row0 + o_base;                 // global row of relative output 0
+	const int w = p.w, h = p.h;
+	const int G2 = (nout + 2 * R + 1) / 2;            // row pairs of the final reduction
+	const int Gin = TWO ? G2 + R : G2;                // row pairs of the input ring
+	const int Gmine = first ? Gin : G2;
+	const int in_row0 = TWO ? Y0 - 2 * R : Y0 - R;    // global row of input pair 0
+	const int gc0 = TWO ? cx0 - 2 * LH : cx0 - LH;    // global column of the first window's first float
+	// the box starts on a bw boundary at or left of gc0 (floor division, gc0 may be negative)
+	const int gxb = (gc0 >= 0 ? gc0 : gc0 - bw + 1) / bw;
+	const int shift = gc0 - gxb * bw;                 // 0 <= shift <= 28, multiple of 4
+
+	if (tid == 0) {
+		for (int i = 0; i < NG; i++) {
+			mbar_init(full_in + 8 * i, 1); mbar_init(empty_in + 8 * i, W);
+			mbar_init(full_t + 8 * i, W); mbar_init(empty_t + 8 * i, W);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("prefetch.tensormap [%0];" :: "l"(&tm) : "memory");
+	}
+	__syncthreads();
+
+	// ---- producer (thread 0): group gi of the input -> ring slot gi mod NG ----
+	const unsigned ring_u32 = smem_u32(ring);
+	const int trow0 = in_row0 - p.src.row0;           // tensor row of input pair 0
+	const int ngroups = (Gin + GP - 1) / GP;
+	auto load_group = [&](int gi) {
+		const int slot = gi % NG;
+		if (gi >= NG) mbar_wait(empty_in + 8 * slot, ((gi / NG) - 1) & 1);
+		mbar_arrive_tx(full_in + 8 * slot, K::GROUP_BYTES);
+		tma_load_4d(ring_u32 + slot * K::GROUP_BYTES, &tm, 0, gxb, trow0 + 2 * GP * gi, plane, full_in + 8 * slot);
+	};
+	if (tid == 0) {
+		for (int gi = 0; gi < NG - 1 && gi < ngroups; gi++) load_group(gi);
+	}
+
+	// ---- consumer state ----
+	float acc[C][K::NACC], hs[C][4];
+#pragma unroll
+	for (int c = 0; c < C; c++) {
+#pragma unroll
+		for (int k = 0; k < K::NACC; k++) acc[c][k] = D::init();
+#pragma unroll
+		for (int k = 0; k < 4; k++) hs[c][k] = D::init();
+	}
+	int zmin = 0;
+	const float *my_ring = reads_input ? ring + shift + C * mt : tring + C * mt;   // this thread's window in slot 0
+	float *my_tmp = tring + C * mt;                                     // first stage: where its temporaries go
+	const unsigned my_full = reads_input ? full_in : full_t;
+	const unsigned my_empty = reads_input ? empty_in : empty_t;
+	const bool lane0 = lane == 0;
+
+	// first stage: this thread's temporary columns, global
+	const int tx = cx0 - LH + C * mt;
+	unsigned tcol_mask = 0;
+#pragma unroll
+	for (int c = 0; c < C; c++) if (tx + c >= 0 && tx + c < w) tcol_mask |= 1u << c;
+	const bool tcol_all = tcol_mask == (1u << C) - 1u;
+	// final stage: output columns
+	const int x = cx0 + C * mt;
+	const bool col_ok = !first && x < w && C * mt < K::OUTW;
+	// running pointers to output row 2g-2R of this thread's columns
+	float *yq = p.y + plane * p.y_pstride + (long long)(Y0 - p.y_row0 - 2 * R) * w + x;
+	const float *xq = p.xop.p ? p.xop.p + plane * p.xop.pstride + (long long)(Y0 - p.xop.row0 - 2 * R) * w + x : nullptr;
+	const float *oq = (!TWO && p.other.p) ? p.other.p + plane * p.other.pstride + (long long)(Y0 - p.other.row0 - 2 * R) * w + x : nullptr;
+	const int epi = p.epi;
+	const bool plain = epi == (ISMAX ? EPI_B : EPI_A);                 // single stage only
+	int gi = 0;                                                        // group being consumed
+	const float *grp = my_ring;                                        // ... and this thread's window in it
+	unsigned grp_empty = my_empty;
+	int tgi = 0;                                                       // first stage: temporary group being written
+	float *tgrp = my_tmp;
+	unsigned tgrp_full = full_t;
+
+#pragma unroll 1
+	for (int g0 = 0; g0 < Gmine; g0 += PERIOD) {
+#pragma unroll
+		for (int s = 0; s < PERIOD; s++) {
+			const int g = g0 + s;
+			if (g < Gmine) {
+				const int pos = s % GP;                                   // place of this pair in its group
+				if (pos == 0) {
+					// a new group: keep the producer one group ahead, then wait for ours
+					const int slot = gi % NG;
+					if (tid == 0 && gi + NG - 1 < ngroups) load_group(gi + NG - 1);
+					mbar_wait_warp(my_full + 8 * slot, (gi / NG) & 1);
+					grp = my_ring + slot * GROUP;
+					grp_empty = my_empty + 8 * slot;
+					gi++;
+				}
+				const float *rowA = grp + pos * PAIR;
+				// the two outputs this step completes
+				const int o0 = 2 * g - 2 * R;
+				const bool e0 = col_ok && o0 >= 0 && o0 < nout;
+				const bool e1 = col_ok && o0 + 1 >= 0 && o0 + 1 < nout;
+				float xv0[C], xv1[C];
+				if (TWO && HASX) {
+					if (e0) load_cols<C>(xq, xv0);
+					if (e1) load_cols<C>(xq + w, xv1);
+				}
+				D::step(acc, hs, s % (R + 1), rowA, rowA + RP, zmin, reads_input,
+					// the group has been read (its loads were issued before this
+					// arrive and complete long before a refill can land)
+					[&]() { if (pos == GP - 1 && lane0) mbar_arrive(grp_empty); },
+					[&](const float (&m0)[C], const float (&m1)[C]) {
+					if (first) {
+						// temporary pair tp = g-R: rows T0+2tp, T0+2tp+1 (T0 = Y0-R), stored negated
+						const int tp = g - R;
+						if (tp < 0) return;
+						const int tpos = ((s - R) % GP + GP) % GP;
+						if (tpos == 0) {
+							const int slot = tgi % NG;
+							if (tgi >= NG) mbar_wait_warp(empty_t + 8 * slot, ((tgi / NG) - 1) & 1);
+							tgrp = my_tmp + slot * GROUP;
+							tgrp_full = full_t + 8 * slot;
+							tgi++;
+						}
+						float *q = tgrp + tpos * PAIR;
+						const int tr = Y0 - R + 2 * tp;
+						float v0[C], v1[C];
+#pragma unroll
+						for (int c = 0; c < C; c++) { v0[c] = -m0[c]; v1[c] = -m1[c]; }
+						if (tcol_all && tr >= 0 && tr + 1 < h) {
+							store_cols<C>(q, v0);
+							store_cols<C>(q + RP, v1);
+						} else {
+							disk_store_tmp_masked(q, q + RP, C, tcol_mask, tr >= 0 && tr < h, tr + 1 >= 0 && tr + 1 < h,
+								v0[0], v0[1], C == 4 ? v0[2] : 0.f, C == 4 ? v0[3] : 0.f,
+								v1[0], v1[1], C == 4 ? v1[2] : 0.f, C == 4 ? v1[3] : 0.f);
+						}
+						if (tpos == GP - 1 || tp == G2 - 1) {
+							__syncwarp();
+							if (lane0) mbar_arrive(tgrp_full);
+						}
+					} else if (TWO) {
+						// result = -m (the temporaries were negated)
+						if (e0) {
+							float v[C];
+#pragma unroll
+							for (int c = 0; c < C; c++)
+								v[c] = !HASX ? -m0[c] : ISMAX ? __fsub_rn(-m0[c], xv0[c]) : __fsub_rn(xv0[c], -m0[c]);
+							store_cols<C>(yq, v);
+						}
+						if (e1) {
+							float v[C];
+#pragma unroll
+							for (int c = 0; c < C; c++)
+								v[c] = !HASX ? -m1[c] : ISMAX ? __fsub_rn(-m1[c], xv1[c]) : __fsub_rn(xv1[c], -m1[c]);
+							store_cols<C>(yq + w, v);
+						}
+					} else {
+						if (e0) {
+							if (plain) store_cols<C>(yq, m0);
+							else disk_emit_general<ISMAX>(yq, xq, oq, epi, C, m0[0], m0[1], C == 4 ? m0[2] : 0.f, C == 4 ? m0[3] : 0.f);
+						}
+						if (e1) {
+							if (plain) store_cols<C>(yq + w, m1);
+							else disk_emit_general<ISMAX>(yq + w, xq ? xq + w : nullptr, oq ? oq + w : nullptr,
+									epi, C, m1[0], m1[1], C == 4 ? m1[2] : 0.f, C == 4 ? m1[3] : 0.f);
+						}
+					}
+				});
+				yq += 2 * w;
+				if ((TWO && HASX) || !TWO) { if (xq) xq += 2 * w; }
+				if (!TWO) { if (oq) oq += 2 * w; }
+			}
+		}
+	}
+	if (__syncthreads_or(zmin == INT_MIN) && tid == 0) atomicOr(p.flag, 1);
+}
+
+// ---- host side --------------------------------------------------------------------
+// Bands: every CTA marches `rows` output rows plus a warm-up of 2*reach rows
+// per stage, and CTAs run in waves of `slots`; pick the band count that
+// minimises waves x (rows + warm-up), i.e. no half-empty last wave.
+static int pick_band_rows(long long slots, int y_rows, long long strips_x_planes, int reach, int stages, double *cost_out)
+{
+	const int warm = 2 * reach * stages + 12;          // rows of warm-up + fixed per-CTA cost
+	const int min_rows = 8 * reach * stages > 32 ? 8 * reach * stages : 32;
+	int best_rows = y_rows;
+	double best = 1e300;
+	for (int bands = 1; bands <= 4096; bands++) {
+		int rows = (y_rows + bands - 1) / bands;
+		rows = (rows + 1) & ~1;
+		if (rows < min_rows && bands > 1) break;
+		const long long ctas = strips_x_planes * ((y_rows + rows - 1) / rows);
+		const long long waves = (ctas + slots - 1) / slots;
+		const double cost = (double)waves * (rows + warm);
+		if (cost < best * 0.999) { best = cost; best_rows = rows; }
+	}
+	if (cost_out) *cost_out = best;
+	return best_rows;
+}
+
+template <class S, int C, int W, bool ISMAX, bool TWO, bool HASX>
+static int disk_occupancy(int device)
+{
+	using K = DiskCfg<S, C, W, TWO>;
+	static int occs[64];                               // per device: 0 = not queried yet
+	int &occ = occs[device & 63];
+	if (occ <= 0) {
+		cudaFuncSetAttribute(k_disk<S, C, W, ISMAX, TWO, HASX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+		int o = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_disk<S, C, W, ISMAX, TWO, HASX>, K::THREADS, K::SMEM) != cudaSuccess || o < 1)
+			o = 1;
+		occ = o;
+	}
+	return occ;
+}
+
+// cost (in marched rows per SM slot, scaled by the warps a CTA keeps busy) of
+// running the job with W warps per stage
+template <class S, int C, int W, bool ISMAX, bool TWO, bool HASX>
+static double disk_plan(const MorsiCtx *c, const DiskArgs &a, int planes, int *band_rows)
+{
+	using K = DiskCfg<S, C, W, TWO>;
+	const int strips = (a.w + K::OUTW - 1) / K::OUTW;
+	const int occ = disk_occupancy<S, C, W, ISMAX, TWO, HASX>(c->device);
+	double cost;
+	*band_rows = pick_band_rows((long long)c->sm_count * occ, a.y_rows, (long long)strips * planes, S::R, TWO ? 2 : 1, &cost);
+	// a CTA's speed is proportional to 1 / (warps resident on its SM)
+	return cost * occ * W;
+}
+
+// The source band as a 4-D tensor (bw, w/bw, rows, planes): dimension 0 is a
+// run of bw contiguous floats, dimension 1 steps over such runs, so a box
+// (bw, RP/bw, nrows, 1) is nrows dense rows of RP floats in shared memory
+// whatever RP is (a plain 2-D box is limited to 256 columns).  Everything
+// outside [0,w) x [0,rows) reads as NaN.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+		const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+		CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int disk_tensor_map(CUtensorMap *tm, const Band &src, int src_rows, int w, int planes, int rp, int nrows, int *bw_out)
+{
+	static EncodeTiledFn encode = nullptr;
+	if (!encode) {
+		void *fn = nullptr;
+		cudaDriverEntryPointQueryResult qres;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+			return morsi_set_error(MORSI_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+		encode = (EncodeTiledFn)fn;
+	}
+	int bw = 32;
+	while (w % bw) bw >>= 1;                           // w % 4 == 0 is a precondition of this path
+	const long long ps = planes > 1 ? src.pstride : (long long)w * src_rows;
+	cuuint64_t dims[4] = {(cuuint64_t)bw, (cuuint64_t)(w / bw), (cuuint64_t)src_rows, (cuuint64_t)planes};
+	cuuint64_t strides[3] = {(cuuint64_t)bw * 4, (cuuint64_t)w * 4, (cuuint64_t)ps * 4};
+	cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)(rp / bw), (cuuint32_t)nrows, 1};
+	cuuint32_t estr[4] = {1, 1, 1, 1};
+	CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)src.p, dims, strides, box, estr,
+			CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+			CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
+	if (r != CUDA_SUCCESS)
+		return morsi_set_error(MORSI_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %dx%dx%d, pitch %lld", (int)r, w, src_rows, planes, ps);
+	*bw_out = bw;
+	return MORSI_OK;
+}
+
+template <class S, int C, int W, bool ISMAX, bool TWO, bool HASX>
+static int disk_launch(const MorsiCtx *c, const DiskArgs &a0, int planes, int band_rows, cudaStream_t st)
+{
+	using K = DiskCfg<S, C, W, TWO>;
+	DiskArgs a = a0;
+	a.band_rows = band_rows;
+	CUtensorMap tm;
+	int bw = 4;
+	int rc = disk_tensor_map(&tm, a.src, a.src_rows, a.w, planes, K::RP, 2 * K::GP, &bw);
+	if (rc) return rc;
+	const int strips = (a.w + K::OUTW - 1) / K::OUTW;
+	dim3 grid(strips, (a.y_rows + band_rows - 1) / band_rows, planes);
+	disk_occupancy<S, C, W, ISMAX, TWO, HASX>(c->device);    // sets the shared-memory attribute once
+	k_disk<S, C, W, ISMAX, TWO, HASX><<<grid, K::THREADS, K::SMEM, st>>>(tm, a, bw);
+	morsi_count_launch(1);
+	MORSI_CU(cudaGetLastError());
+	return MORSI_OK;
+}
+
+static int disk_forced_w()
+{
+	const char *s = getenv("MORSI_DISK_W");            // 2 or 4 warps per stage; default: planned
+	return s ? atoi(s) : 0;
+}
+
+template <class S, int C, bool ISMAX, bool TWO, bool HASX>
+static int disk_run(MorsiCtx *c, const DiskArgs &a, int planes, cudaStream_t st)
+{
+	int rows2 = 0, rows4 = 0;
+	const double c2 = disk_plan<S, C, 2, ISMAX, TWO, HASX>(c, a, planes, &rows2);
+	const double c4 = disk_plan<S, C, 4, ISMAX, TWO, HASX>(c, a, planes, &rows4);
+	const int force = disk_forced_w();
+	if (force == 2 || (force != 4 && c2 < c4))
+		return disk_launch<S, C, 2, ISMAX, TWO, HASX>(c, a, planes, rows2, st);
+	return disk_launch<S, C, 4, ISMAX, TWO, HASX>(c, a, planes, rows4, st);
+}
+
+template <int ID>
+static int disk_shape(MorsiCtx *c, const DiskArgs &a, int planes, bool ismax, bool two, cudaStream_t st)
+{
+	constexpr int C = 4;
+	using S = Shape<ID>;
+	if (two && a.xop.p)
+		return ismax ? disk_run<S, C, true, true, true>(c, a, planes, st) : disk_run<S, C, false, true, true>(c, a, planes, st);
+	if (two)
+		return ismax ? disk_run<S, C, true, true, false>(c, a, planes, st) : disk_run<S, C, false, true, false>(c, a, planes, st);
+	return ismax ? disk_run<S, C, true, false, false>(c, a, planes, st) : disk_run<S, C, false, false, false>(c, a, planes, st);
+}
+
+// development aid: -DMORSI_DISK_IDS="T(8) T(13)" compiles a subset of the shapes
+#ifdef MORSI_DISK_IDS
+#define DISK_IDS MORSI_DISK_IDS
+#else
+#define DISK_IDS T(0) T(1) T(2) T(3) T(4) T(5) T(6) T(7) T(8) T(9) T(10) T(11) T(12) T(13)
+#endif
+
+template <int ID>
+static bool shape_matches(const RowRunPlan &rr)
+{
+	if (rr.reach != Shape<ID>::R) return false;
+	for (int i = 0; i <= 2 * rr.reach; i++)
+		if (rr.hw[i] != Shape<ID>::hw(i)) return false;
+	return true;
+}
+
+static int find_shape(const RowRunPlan &rr)
+{
+	if (!rr.ok) return -1;
+#define T(ID) if (shape_matches<ID>(rr)) return ID;
+	DISK_IDS
+#undef T
+	return -1;
+}
+
+static int launch_by_id(int id, MorsiCtx *c, const DiskArgs &a, int planes, bool ismax, bool two, cudaStream_t st)
+{
+	switch (id) {
+#define T(ID) case ID: return disk_shape<ID>(c, a, planes, ismax, two, st);
+	DISK_IDS
+#undef T
+	}
+	return morsi_set_error(MORSI_ERR_INVALID, "no such shape %d", id);
+}
+
+// One reduction pass over `src` for output rows [row0,row0+rows) into `dst`.
+static int disk_pass(MorsiCtx *c, int id, bool ismax, int epi, const MorsiJob &job, Band src, int src_rows,
+		Band xop, Band other, float *dst, long long dst_pstride, int row0, int rows, int *flag)
+{
+	DiskArgs a;
+	a.src = src; a.src_rows = src_rows; a.xop = xop; a.other = other;
+	a.y = dst; a.y_pstride = dst_pstride; a.y_row0 = row0; a.y_rows = rows;
+	a.w = job.w; a.h = job.h; a.epi = epi; a.flag = flag; a.band_rows = rows;
+	return launch_by_id(id, c, a, job.planes, ismax, false, job.stream);
+}
+
+int morsi_run_disk(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled)
+{
+	*handled = 0;
+	const OpPlan plan = morsi_op_plan(job.op);
+	if (plan.special) return MORSI_OK;
+	const int id = find_shape(de->rowrun);
+	if (id < 0) return MORSI_OK;
+	const bool aligned = (job.w % 4 == 0) && (((uintptr_t)job.x) % 16 == 0) && (((uintptr_t)job.y) % 16 == 0)
+		&& (job.x_pstride % 4 == 0) && (job.y_pstride % 4 == 0);
+	if (!aligned) return MORSI_OK;
+	const int R = de->rowrun.reach;
+	const Band none{nullptr, 0, 0};
+	const Band xb{job.x, job.x_row0, job.x_pstride};
+	int rc;
+
+	// how many temporaries does the plan need?
+	//   1 stage, one side      : 0      (erosion, dilation, i/egradient, i/eblur)
+	//   1 stage, both sides    : 1      (gradient, laplacian, enhance, blur, cblur: a = erosion)
+	//   2 stages               : 0      (opening, closing, tophat, bothat: fused)
+	//   oscillation            : 3
+	const bool both1 = plan.stages == 1 && plan.a_from && plan.b_from;
+	const bool osc = plan.t_min && plan.t_max;
+	if (plan.stages == 1 && !both1) {
+		rc = disk_pass(c, id, plan.b_from != 0, plan.epi, job, xb, job.x_rows, xb, none,
+				job.y, job.y_pstride, job.y_row0, job.y_rows, flag);
+		if (rc) return rc;
+		*handled = 1;
+		return MORSI_OK;
+	}
+	if (plan.stages == 2 && !osc) {
+		// opening, closing, tophat, bothat: both stages in one kernel
+		DiskArgs a;
+		a.src = xb; a.src_rows = job.x_rows; a.other = none;
+		a.xop = (plan.epi == EPI_X_SUB_B || plan.epi == EPI_A_SUB_X) ? xb : none;
+		a.y = job.y; a.y_pstride = job.y_pstride; a.y_row0 = job.y_row0; a.y_rows = job.y_rows;
+		a.w = job.w; a.h = job.h; a.epi = plan.epi; a.flag = flag; a.band_rows = job.y_rows;
+		rc = launch_by_id(id, c, a, job.planes, plan.t_max != 0, true, job.stream);
+		if (rc) return rc;
+		*handled = 1;
+		return MORSI_OK;
+	}
+	// temporaries cover the output band grown by one reach (clipped); chunk the
+	// band so that a temporary stays below 512 MiB
+	const long long budget = 512LL << 20;
+	long long rows_fit = budget / ((long long)job.w * 4 * job.planes) - 2 * R;
+	if (rows_fit < 8 * R + 64) rows_fit = 8 * R + 64;
+	const int chunk = (int)(rows_fit < job.y_rows ? rows_fit : job.y_rows);
+	for (int r0 = 0; r0 < job.y_rows; r0 += chunk) {
+		const int o0 = job.y_row0 + r0;
+		const int orows = job.y_rows - r0 < chunk ? job.y_rows - r0 : chunk;
+		float *ydst = job.y + (long long)r0 * job.w;
+		if (both1) {
+			void *p0; if ((rc = morsi_ws_get(c, job.lane, 0, (size_t)job.w * orows * job.planes * 4, &p0))) return rc;
+			const long long tps = (long long)job.w * orows;
+			rc = disk_pass(c, id, false, EPI_A, job, xb, job.x_rows, none, none, (float *)p0, tps, o0, orows, flag);
+			if (rc) return rc;
+			rc = disk_pass(c, id, true, plan.epi, job, xb, job.x_rows, xb, Band{(float *)p0, o0, tps},
+					ydst, job.y_pstride, o0, orows, flag);
+			if (rc) return rc;
+			continue;
+		}
+		// oscillation = closing - opening: erosion and dilation of x, then the
+		// opposite reductions, the last one subtracting
+		int t0 = o0 - R; if (t0 < 0) t0 = 0;
+		int t1 = o0 + orows + R; if (t1 > job.h) t1 = job.h;
+		const int trows = t1 - t0;
+		const long long tps = (long long)job.w * trows;
+		const size_t tbytes = (size_t)tps * job.planes * 4;
+		void *p0, *p1, *p2;
+		if ((rc = morsi_ws_get(c, job.lane, 0, tbytes, &p0))) return rc;
+		if ((rc = morsi_ws_get(c, job.lane, 1, tbytes, &p1))) return rc;
+		if ((rc = morsi_ws_get(c, job.lane, 2, (size_t)job.w * orows * job.planes * 4, &p2))) return rc;
+		const long long ops = (long long)job.w * orows;
+		rc = disk_pass(c, id, false, EPI_A, job, xb, job.x_rows, none, none, (float *)p0, tps, t0, trows, flag);
+		if (rc) return rc;
+		rc = disk_pass(c, id, true, EPI_B, job, xb, job.x_rows, none, none, (float *)p1, tps, t0, trows, flag);
+		if (rc) return rc;
+		rc = disk_pass(c, id, true, EPI_B, job, Band{(float *)p0, t0, tps}, trows, none, none,
+				(float *)p2, ops, o0, orows, flag);
+		if (rc) return rc;
+		rc = disk_pass(c, id, false, EPI_A_SUB_B, job, Band{(float *)p1, t0, tps}, trows, none,
+				Band{(float *)p2, o0, ops}, ydst, job.y_pstride, o0, orows, flag);
+		if (rc) return rc;
+	}
+	*handled = 1;
+	return MORSI_OK;
+}

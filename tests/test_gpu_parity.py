@@ -75,6 +75,35 @@ def test_vs_oracle_shapes_elements_ops(dist):
                 assert_same(M.apply(op, e, x), o.apply(op, e, x), f"{name} {op} {w}x{h} dist={dist}")
 
 
+DISKS = ["disk2.5", "disk3", "disk3.5", "disk4", "disk4.2", "disk5", "disk5.1", "disk6", "disk7", "disk8",
+         "disk9", "disk10", "disk12", "disk15"]
+
+
+@pytest.mark.parametrize("warps", ["2", "4"])
+def test_disk_kernels_multi_strip_multi_band(warps, monkeypatch):
+    """every compiled disk shape of k_disk.cu on an image wide and tall enough for
+    several column strips and row bands per plane; both CTA sizes; the min/max
+    operations incl. the fused two-stage ones; NaN / Inf / +-0 sprinkled in plane 1"""
+    monkeypatch.setenv("MORSI_DISK_W", warps)
+    o = oracle()
+    h, w = 420, 1100 if warps == "4" else 600
+    x = np.stack([M.synth_host(w, h, plane=p, seed=33, dist=2 if p == 1 else 0) for p in range(2)])
+    x[0, 100:180, 200:330] = np.nan          # all-NaN windows for the small disks
+    x[x == 0] = 0.0                          # no -0.0: the result must come from the fast kernels
+    assert not np.any(x.view(np.uint32) == 0x80000000)
+    xz = M.synth_host(w, 150, seed=34, dist=2)   # with -0.0: flag raised, order-preserving re-run
+    for name in ("disk5", "disk7"):
+        for op in ("opening", "dilation"):
+            assert_same(M.apply(op, o.element(name), xz), o.apply(op, o.element(name), xz), f"{name} {op} -0")
+    for name in DISKS:
+        e = o.element(name)
+        ops = ["erosion", "dilation", "opening", "closing", "tophat", "bothat"]
+        if name in ("disk4.2", "disk7", "disk15"):
+            ops += ["gradient", "oscillation", "cblur", "igradient"]
+        for op in ops:
+            assert_same(M.apply(op, e, x), o.apply(op, e, x), f"{name} {op} {w}x{h} W={warps}")
+
+
 def test_all_nan_windows_and_constant_images():
     """windows with no usable neighbour give +-INF (src/morsi.c:63,77), also on the fast paths"""
     o = oracle()
