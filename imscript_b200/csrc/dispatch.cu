@@ -52,7 +52,7 @@ static dim3 exact_grid(int w, int rows, int planes, bool gated)
 	unsigned gy = (unsigned)((rows + 7) / 8);
 	if (gy > 16384) gy = 16384;
 	if (gated) {
-		unsigned long long cap = 148ull * 16;
+		unsigned long long cap = 148ull * 4;   // a no-op grid costs per CTA: keep it to a few per SM
 		unsigned long long per_row = (unsigned long long)gx * (unsigned)planes;
 		unsigned want = (unsigned)(cap / (per_row ? per_row : 1));
 		if (want < 1) want = 1;

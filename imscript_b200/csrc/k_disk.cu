@@ -208,7 +208,10 @@ struct DiskCfg {
 #ifndef DISK_REGS_SMALL
 #define DISK_REGS_SMALL 168
 #endif
-	static constexpr int REGS = (C * (2 * R + 2) > 64) ? 255 : DISK_REGS_SMALL;
+#ifndef DISK_REGS_C2
+#define DISK_REGS_C2 84
+#endif
+	static constexpr int REGS = (C * (2 * R + 2) > 64) ? 255 : (C == 2 ? (C * (2 * R + 2) > 36 ? 128 : DISK_REGS_C2) : DISK_REGS_SMALL);
 	static constexpr int MINB = 65536 / (REGS * THREADS) > 0 ? 65536 / (REGS * THREADS) : 1;
 };
 
@@ -556,10 +559,22 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 // minimises waves x (rows + warm-up), i.e. no half-empty last wave.
 static int pick_band_rows(long long slots, int y_rows, long long strips_x_planes, int reach, int stages, double *cost_out)
 {
-	const int warm = 2 * reach * stages + 12;          // rows of warm-up + fixed per-CTA cost
+	// rows of warm-up + fixed per-CTA cost.  The two stages of a fused CTA warm
+	// up side by side (different warps), so the measured cost is one stage's:
+	// C2 on B200 (51 strip-planes, 444 CTA slots): 8 bands 0.324 ms, 17 bands
+	// 0.299 ms, 26 bands 0.298 ms, 9 bands 0.373 ms (a barely started 2nd wave).
+	(void)stages;
+	const int warm = 2 * reach + 12;
 	const int min_rows = 8 * reach * stages > 32 ? 8 * reach * stages : 32;
 	int best_rows = y_rows;
 	double best = 1e300;
+	static const int forced_bands = getenv("MORSI_DISK_BANDS") ? atoi(getenv("MORSI_DISK_BANDS")) : 0;   // experiments
+	if (forced_bands > 0) {
+		int rows = (y_rows + forced_bands - 1) / forced_bands;
+		rows = (rows + 1) & ~1;
+		if (cost_out) *cost_out = 1.0;
+		return rows;
+	}
 	for (int bands = 1; bands <= 4096; bands++) {
 		int rows = (y_rows + bands - 1) / bands;
 		rows = (rows + 1) & ~1;
@@ -675,16 +690,25 @@ static int disk_run(MorsiCtx *c, const DiskArgs &a, int planes, cudaStream_t st)
 	return disk_launch<S, C, 4, ISMAX, TWO, HASX>(c, a, planes, rows4, st);
 }
 
-template <int ID>
-static int disk_shape(MorsiCtx *c, const DiskArgs &a, int planes, bool ismax, bool two, cudaStream_t st)
+template <int ID, int C>
+static int disk_shape_c(MorsiCtx *c, const DiskArgs &a, int planes, bool ismax, bool two, cudaStream_t st)
 {
-	constexpr int C = 4;
 	using S = Shape<ID>;
 	if (two && a.xop.p)
 		return ismax ? disk_run<S, C, true, true, true>(c, a, planes, st) : disk_run<S, C, false, true, true>(c, a, planes, st);
 	if (two)
 		return ismax ? disk_run<S, C, true, true, false>(c, a, planes, st) : disk_run<S, C, false, true, false>(c, a, planes, st);
 	return ismax ? disk_run<S, C, true, false, false>(c, a, planes, st) : disk_run<S, C, false, false, false>(c, a, planes, st);
+}
+
+template <int ID>
+static int disk_shape(MorsiCtx *c, const DiskArgs &a, int planes, bool ismax, bool two, cudaStream_t st)
+{
+#ifdef MORSI_DISK_EXPERIMENT_C2
+	static const bool c2 = getenv("MORSI_DISK_C") && atoi(getenv("MORSI_DISK_C")) == 2;
+	if (c2) return disk_shape_c<ID, 2>(c, a, planes, ismax, two, st);
+#endif
+	return disk_shape_c<ID, 4>(c, a, planes, ismax, two, st);
 }
 
 // development aid: -DMORSI_DISK_IDS="T(8) T(13)" compiles a subset of the shapes

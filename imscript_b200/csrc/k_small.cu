@@ -12,6 +12,8 @@
 // exactly like fmin/fmax; they are not order-preserving for +0/-0, so any -0.0
 // seen in the loaded data raises *flag and the dispatcher re-runs the
 // order-preserving kernels.
+#include <cstdlib>
+
 #include "dispatch.cuh"
 
 struct SmallArgs {
@@ -22,6 +24,7 @@ struct SmallArgs {
 	int w, h;
 	unsigned mask;      // bit (dy+1)*3+(dx+1)
 	int rows_per_warp;
+	int wx_log2;        // k_small_1: 2^wx_log2 warps of a CTA sit side by side on the same rows
 	int epi;            // Epi
 	int stage1_min, stage1_max;   // two-stage: which temporaries exist
 	int need_a, need_b;           // final pass: erosion side / dilation side
@@ -155,52 +158,72 @@ __device__ __forceinline__ void store_row(float *yrow, int x0, int w, const floa
 }
 
 // ---- single stage -----------------------------------------------------------
-// Branch-free row fetch for the single-stage kernel: one predicated float4
-// load per lane plus one predicated scalar load on the two edge lanes of the
-// warp (lane 0: column x0-1, lane 31: column x0+4).
+// Row fetch for the single-stage kernel.  The loads are UNCONDITIONAL (an
+// absent row or column reads a valid dummy address instead) and the NaN of an
+// absent sample is selected when the row is consumed: a predicated load that
+// merges into a NaN-initialised register makes the compiler funnel every
+// prefetch slot through one register and wait for the load right after it was
+// issued, which defeats the prefetch (seen in the round-1 ncu source view).
 struct Raw1 { float4 q; float e; };
 
 template <bool VEC>
-__device__ __forceinline__ void fetch1(const float *row, bool row_ok, bool col_ok, bool edge_ok, int eoff,
-		int w, int x0, Raw1 &r)
+__device__ __forceinline__ void fetch1(const float *row, const float *dummy, bool row_ok, bool col_ok, bool edge_ok,
+		int eoff, int w, int x0, Raw1 &r)
 {
-	const float nan = CUDART_NAN_F;
-	r.q = make_float4(nan, nan, nan, nan);
-	r.e = nan;
 	if (VEC) {
-		if (row_ok && col_ok) r.q = __ldg(reinterpret_cast<const float4 *>(row));
+		const float *q = (row_ok && col_ok) ? row : dummy;
+		const float *e = (row_ok && edge_ok) ? row + eoff : dummy;
+		r.q = __ldg(reinterpret_cast<const float4 *>(q));
+		r.e = __ldg(e);
 	} else {
+		const float nan = CUDART_NAN_F;
+		r.q = make_float4(nan, nan, nan, nan);
+		r.e = nan;
 		if (row_ok && x0 < w) r.q.x = __ldg(row);
 		if (row_ok && x0 + 1 < w) r.q.y = __ldg(row + 1);
 		if (row_ok && x0 + 2 < w) r.q.z = __ldg(row + 2);
 		if (row_ok && x0 + 3 < w) r.q.w = __ldg(row + 3);
+		if (row_ok && edge_ok) r.e = __ldg(row + eoff);
 	}
-	if (row_ok && edge_ok) r.e = __ldg(row + eoff);
 }
 
-__device__ __forceinline__ void assemble1(const Raw1 &r, int lane, float (&v)[6], unsigned &negzero)
+// ok / eok: the row's samples / its edge sample exist (VEC only; the scalar
+// path stored NaN at fetch time)
+template <bool VEC>
+__device__ __forceinline__ void assemble1(const Raw1 &r, bool ok, bool eok, int lane, float (&v)[6], unsigned &negzero)
 {
-	negzero |= (__float_as_uint(r.q.x) == 0x80000000u) | (__float_as_uint(r.q.y) == 0x80000000u) |
-	           (__float_as_uint(r.q.z) == 0x80000000u) | (__float_as_uint(r.q.w) == 0x80000000u) |
-	           (__float_as_uint(r.e) == 0x80000000u);
-	const float l1 = __shfl_up_sync(0xffffffffu, r.q.w, 1);
-	const float r1 = __shfl_down_sync(0xffffffffu, r.q.x, 1);
-	v[0] = lane == 0 ? r.e : l1;
-	v[1] = r.q.x; v[2] = r.q.y; v[3] = r.q.z; v[4] = r.q.w;
-	v[5] = lane == 31 ? r.e : r1;
+	const float nan = CUDART_NAN_F;
+	float4 q = r.q;
+	float e = r.e;
+	if (VEC) {
+		if (!ok) q = make_float4(nan, nan, nan, nan);
+		if (!eok) e = nan;
+	}
+	negzero |= (__float_as_uint(q.x) == 0x80000000u) | (__float_as_uint(q.y) == 0x80000000u) |
+	           (__float_as_uint(q.z) == 0x80000000u) | (__float_as_uint(q.w) == 0x80000000u) |
+	           (__float_as_uint(e) == 0x80000000u);
+	const float l1 = __shfl_up_sync(0xffffffffu, q.w, 1);
+	const float r1 = __shfl_down_sync(0xffffffffu, q.x, 1);
+	v[0] = lane == 0 ? e : l1;
+	v[1] = q.x; v[2] = q.y; v[3] = q.z; v[4] = q.w;
+	v[5] = lane == 31 ? e : r1;
 }
 
 // EPI >= 0: the epilogue (and with it which of min / max is needed) is a
 // compile-time constant; EPI < 0: taken from p.epi at run time.
-template <int MASK, bool VEC, int EPI>
+// PF: rows in flight per thread (a multiple of 3).  The 8 warps of a CTA are
+// laid out 2^wx_log2 side by side (adjacent 128-column spans of the same rows:
+// longer contiguous runs per DRAM page) by 8 >> wx_log2 row segments.
+template <int MASK, bool VEC, int EPI, int PF>
 __global__ void __launch_bounds__(256) k_small_1(SmallArgs p)
 {
 	const int lane = threadIdx.x;
-	const int x0 = (blockIdx.x * 32 + lane) * 4;
+	const int wxm = (1 << p.wx_log2) - 1;
+	const int x0 = (((blockIdx.x << p.wx_log2) + (threadIdx.y & wxm)) * 32 + lane) * 4;
 	const int plane = blockIdx.z;
-	const int seg = blockIdx.y * blockDim.y + threadIdx.y;
+	const int seg = blockIdx.y * (blockDim.y >> p.wx_log2) + (threadIdx.y >> p.wx_log2);
 	const int jj0 = seg * p.rows_per_warp;
-	if (jj0 >= p.y_rows) return;
+	if (jj0 >= p.y_rows || x0 - 4 * lane >= p.w) return;      // the whole warp: no barrier in this kernel
 	const int jj1 = min(p.y_rows, jj0 + p.rows_per_warp);
 	const int y0 = p.y_row0 + jj0, y1 = p.y_row0 + jj1;
 	const int w = p.w, h = p.h;
@@ -210,7 +233,8 @@ __global__ void __launch_bounds__(256) k_small_1(SmallArgs p)
 	const bool need_b = CT ? EpiNeeds<CT ? EPI : 0>::b : (p.need_b != 0);
 
 	// running pointers: next row to fetch, next row to store
-	const float *fp = p.x.p + plane * p.x.pstride + (long long)(y0 - 1 - p.x.row0) * w + x0;
+	const float *dummy = p.x.p + plane * p.x.pstride;          // always readable, 16-byte aligned
+	const float *fp = dummy + (long long)(y0 - 1 - p.x.row0) * w + x0;
 	int fj = y0 - 1;                                  // global row fp points at
 	float *yq = p.y + plane * p.y_pstride + (long long)(y0 - p.y_row0) * w + x0;
 
@@ -220,28 +244,30 @@ __global__ void __launch_bounds__(256) k_small_1(SmallArgs p)
 	const bool edge_ok = (lane == 0 && x0 > 0 && x0 - 1 < w) || (lane == 31 && x0 + 4 < w);
 
 	float in[3][6];
-	Raw1 raw[SMALL_PF];
-	// input rows j = y0-1 .. y1 ; window slot of row j is (j-(y0-1)) % 3 and its
-	// prefetch slot the same (SMALL_PF == 3); rows are fetched SMALL_PF ahead,
-	// never below row y1 (the source band may end there)
+	Raw1 raw[PF];
+	// input rows j = y0-1 .. y1; window slot of row j is (j-(y0-1)) % 3, its
+	// prefetch slot (j-(y0-1)) % PF; rows are fetched PF ahead, never below
+	// row y1 (the source band may end there)
+#define ROW_OK(j) ((unsigned)(j) < (unsigned)h && (j) <= y1)
 #pragma unroll
-	for (int k = 0; k < SMALL_PF; k++) {
-		fetch1<VEC>(fp, (unsigned)fj < (unsigned)h && fj <= y1, col_ok, edge_ok, eoff, w, x0, raw[k]);
+	for (int k = 0; k < PF; k++) {
+		fetch1<VEC>(fp, dummy, ROW_OK(fj), col_ok, edge_ok, eoff, w, x0, raw[k]);
 		fp += w; fj++;
 	}
-	assemble1(raw[0], lane, in[0], negzero);
-	fetch1<VEC>(fp, (unsigned)fj < (unsigned)h && fj <= y1, col_ok, edge_ok, eoff, w, x0, raw[0]);
+	assemble1<VEC>(raw[0], ROW_OK(y0 - 1) && col_ok, ROW_OK(y0 - 1) && edge_ok, lane, in[0], negzero);
+	fetch1<VEC>(fp, dummy, ROW_OK(fj), col_ok, edge_ok, eoff, w, x0, raw[0]);
 	fp += w; fj++;
-	assemble1(raw[1], lane, in[1], negzero);
-	fetch1<VEC>(fp, (unsigned)fj < (unsigned)h && fj <= y1, col_ok, edge_ok, eoff, w, x0, raw[1]);
+	assemble1<VEC>(raw[1], ROW_OK(y0) && col_ok, ROW_OK(y0) && edge_ok, lane, in[1], negzero);
+	fetch1<VEC>(fp, dummy, ROW_OK(fj), col_ok, edge_ok, eoff, w, x0, raw[1]);
 	fp += w; fj++;
-	for (int jb = y0 + 1; jb <= y1; jb += 3) {
+	for (int jb = y0 + 1; jb <= y1; jb += PF) {
 #pragma unroll
-		for (int u = 0; u < 3; u++) {
-			const int j = jb + u;               // slot (u+2)%3
+		for (int u = 0; u < PF; u++) {
+			const int j = jb + u;               // row slot (u+2)%3, prefetch slot (u+2)%PF
 			if (j <= y1) {
-				assemble1(raw[(u + 2) % 3], lane, in[(u + 2) % 3], negzero);
-				fetch1<VEC>(fp, (unsigned)fj < (unsigned)h && fj <= y1, col_ok, edge_ok, eoff, w, x0, raw[(u + 2) % 3]);
+				const bool rok = ROW_OK(j);
+				assemble1<VEC>(raw[(u + 2) % PF], rok && col_ok, rok && edge_ok, lane, in[(u + 2) % 3], negzero);
+				fetch1<VEC>(fp, dummy, ROW_OK(fj), col_ok, edge_ok, eoff, w, x0, raw[(u + 2) % PF]);
 				fp += w; fj++;
 				const float (&up)[6] = in[u % 3];
 				const float (&mid)[6] = in[(u + 1) % 3];
@@ -260,6 +286,7 @@ __global__ void __launch_bounds__(256) k_small_1(SmallArgs p)
 			}
 		}
 	}
+#undef ROW_OK
 	if (__any_sync(0xffffffffu, negzero) && lane == 0) atomicOr(p.flag, 1);
 }
 
@@ -357,19 +384,26 @@ __global__ void __launch_bounds__(256) k_small_2(SmallArgs p)
 }
 
 // ---- host side ------------------------------------------------------------------
+static int small_pf()
+{
+	static const int pf = getenv("MORSI_SMALL_PF") ? atoi(getenv("MORSI_SMALL_PF")) : 3;
+	return pf;
+}
+
 template <int MASK, bool VEC>
 static void launch_small_t(const SmallArgs &a, int stages, bool osc, dim3 grid, dim3 block, cudaStream_t s)
 {
 	if (stages == 1) {
 		if (VEC) {
+			const bool pf3 = small_pf() == 3;
 			switch (a.epi) {
-#define E(X) case X: k_small_1<MASK, VEC, X><<<grid, block, 0, s>>>(a); return;
+#define E(X) case X: if (pf3) k_small_1<MASK, VEC, X, 3><<<grid, block, 0, s>>>(a); else k_small_1<MASK, VEC, X, 6><<<grid, block, 0, s>>>(a); return;
 			E(EPI_A) E(EPI_B) E(EPI_B_SUB_A) E(EPI_X_SUB_A) E(EPI_B_SUB_X) E(EPI_LAP) E(EPI_ENH) E(EPI_BLUR)
 			E(EPI_IBLUR) E(EPI_EBLUR) E(EPI_CBLUR)
 #undef E
 			}
 		}
-		k_small_1<MASK, VEC, -1><<<grid, block, 0, s>>>(a);
+		k_small_1<MASK, VEC, -1, 3><<<grid, block, 0, s>>>(a);
 	}
 	else if (osc) k_small_2<MASK, VEC, true><<<grid, block, 0, s>>>(a);
 	else k_small_2<MASK, VEC, false><<<grid, block, 0, s>>>(a);
@@ -391,14 +425,30 @@ int morsi_run_small(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int 
 	const bool osc = plan.t_min && plan.t_max;
 	const bool vec = (job.w % 4 == 0) && (((uintptr_t)job.x) % 16 == 0) && (((uintptr_t)job.y) % 16 == 0)
 		&& (job.x_pstride % 4 == 0) && (job.y_pstride % 4 == 0);
-	// rows per warp: long marches amortise the warm-up rows, but keep >= ~4 CTAs per SM
-	const int gx = (job.w + 127) / 128;
-	int rpw = 64;
-	while (rpw > 8 && (long long)gx * ((job.y_rows + rpw * 8 - 1) / (rpw * 8)) * job.planes < 4LL * c->sm_count)
+	// single stage: the warps of a CTA side by side (as many as the width feeds)
+	int wxl = 0;
+	if (plan.stages == 1) {
+		static const int forced = getenv("MORSI_SMALL_WX") ? atoi(getenv("MORSI_SMALL_WX")) : -1;
+		while (wxl < 3 && (128 << (wxl + 1)) <= job.w + 127) wxl++;
+		if (forced >= 0 && forced <= 3) wxl = forced;
+	}
+	a.wx_log2 = wxl;
+	const int segs = 8 >> wxl;                         // row segments per CTA
+	// Rows per warp.  Single stage: SHORT marches measure best on B200 (C5: 8 rows
+	// 76 % of the HBM copy rate, 64 rows 72 %, 270 rows 60 %): the CTAs in flight
+	// then sweep the image like a copy does and the re-read halo rows hit in L2;
+	// small images get even shorter marches so that every SM has warps to run.
+	// Two stages: longer marches, the warm-up is 4 rows of two reductions.
+	const int gx = (job.w + (128 << wxl) - 1) / (128 << wxl);
+	static const int forced_rpw = getenv("MORSI_SMALL_RPW") ? atoi(getenv("MORSI_SMALL_RPW")) : 0;
+	int rpw = plan.stages == 1 ? 8 : 64;
+	const int min_rpw = plan.stages == 1 ? 2 : 8;
+	while (rpw > min_rpw && (long long)gx * ((job.y_rows + rpw * segs - 1) / (rpw * segs)) * job.planes < 4LL * c->sm_count)
 		rpw /= 2;
+	if (forced_rpw > 0) rpw = forced_rpw;
 	a.rows_per_warp = rpw;
 	dim3 block(32, 8);
-	dim3 grid(gx, (job.y_rows + rpw * 8 - 1) / (rpw * 8), job.planes);
+	dim3 grid(gx, (job.y_rows + rpw * segs - 1) / (rpw * segs), job.planes);
 	const unsigned CROSS = 0272u /* .#. ### .#. */, SQUARE = 0777u;
 	if (vec) {
 		if (a.mask == CROSS) launch_small_t<(int)0272, true>(a, plan.stages, osc, grid, block, job.stream);

@@ -107,3 +107,32 @@ class BandJob:
     def step(self):
         self.exchange()
         self.compute()
+
+    # ---- end to end: the band lives in (pinned) HOST memory -----------------
+    def host_buffers(self):
+        """Pinned host copies of the owned input rows and of the output band."""
+        p, L = self.plan, self.L
+        self.h_x, self.h_y = B._vp(), B._vp()
+        nbytes = p.rows_own * self.w * 4
+        B.check(L.morsi_cuda_host_alloc(ctypes.byref(self.h_x), nbytes))
+        B.check(L.morsi_cuda_host_alloc(ctypes.byref(self.h_y), nbytes))
+        own = self.x_ptr + p.own_offset * self.w * 4
+        B.check(L.morsi_cuda_memcpy_d2h(self.h_x, own, nbytes, self.stream))
+        B.check(L.morsi_cuda_sync(self.stream))
+        return nbytes
+
+    def e2e_step(self):
+        """host -> device copy of the owned rows, halo exchange between the
+        ranks, the kernels, device -> host copy of the result, all on one stream"""
+        p, L = self.plan, self.L
+        nbytes = p.rows_own * self.w * 4
+        own = self.x_ptr + p.own_offset * self.w * 4
+        B.check(L.morsi_cuda_memcpy_h2d(own, self.h_x, nbytes, self.stream))
+        self.exchange()
+        self.compute()
+        B.check(L.morsi_cuda_memcpy_d2h(self.h_y, self.y_ptr, nbytes, self.stream))
+        B.check(L.morsi_cuda_sync(self.stream))
+
+    def free_host_buffers(self):
+        self.L.morsi_cuda_host_free(self.h_x)
+        self.L.morsi_cuda_host_free(self.h_y)

@@ -39,6 +39,20 @@ __global__ void __launch_bounds__(512) k(float *out, int iters, float s0, float 
 				if (MODE == 8) { asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c));
 				                 asm volatile("xor.b32 %0, %0, %1;" : "+r"(ic) : "r"(ia[i])); }
 				if (MODE == 9) asm volatile("add.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b));
+				if (MODE == 10) asm volatile("{.reg .s32 t; min.s32 t, %0, %1; min.s32 %0, t, %2;}" : "+r"(ia[i]) : "r"(ib), "r"(ic));
+				if (MODE == 11) { asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c));
+				                  asm volatile("{.reg .s32 t; min.s32 t, %0, %1; min.s32 %0, t, %2;}" : "+r"(ia[i]) : "r"(ib), "r"(ic)); }
+				if (MODE == 12) { asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c));
+				                  asm volatile("add.f32 %0, %0, %1;" : "+f"(f) : "f"(b)); }
+				if (MODE == 13) asm volatile("min.f16x2 %0, %0, %1;" : "+r"(ia[i]) : "r"(ib));
+				if (MODE == 14) { asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c));
+				                  asm volatile("min.f16x2 %0, %0, %1;" : "+r"(ia[i]) : "r"(ib)); }
+				if (MODE == 15) { asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b), "f"(c));
+				                  asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(a[(i+4)&7]) : "f"(c), "f"(b));
+				                  asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(b), "f"(c));
+				                  asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(ic) : "r"(ib), "r"(ib)); }
+				if (MODE == 16) asm volatile("min.u32 %0, %0, %1;" : "+r"(ia[i]) : "r"(ib));
+				if (MODE == 17) asm volatile("{.reg .pred p; setp.lt.f32 p, %0, %1; selp.f32 %0, %0, %1, p;}" : "+f"(a[i]) : "f"(b));
 			}
 		}
 	}
@@ -76,5 +90,13 @@ int main()
 	run<5>("FMNMX3 + LDS.128 4:1 (count FMNMX)", 1);
 	run<8>("FMNMX3 + LOP3 1:1 (count both)", 2);
 	run<9>("FADD", 1);
+	run<10>("VIMNMX3 s32 3-input", 1);
+	run<11>("FMNMX3 + VIMNMX3 1:1 (count both)", 2);
+	run<12>("FMNMX3 + FADD 1:1 (count both)", 2);
+	run<13>("HMNMX2 f16x2", 1);
+	run<14>("FMNMX3 + HMNMX2 1:1 (count both)", 2);
+	run<15>("2 FMNMX3 + FFMA + IMAD (count all 4)", 4);
+	run<16>("IMNMX u32 2-input", 1);
+	run<17>("FSETP+FSEL (count pair as 1)", 1);
 	return 0;
 }

@@ -104,6 +104,22 @@ def test_disk_kernels_multi_strip_multi_band(warps, monkeypatch):
             assert_same(M.apply(op, e, x), o.apply(op, e, x), f"{name} {op} {w}x{h} W={warps}")
 
 
+@pytest.mark.parametrize("quad", ["1", "0"])
+def test_median_fast_kernels(quad, monkeypatch):
+    """median by every disk the shared-window kernel (k_median_quad) and the
+    per-pixel kernel (k_median_fast) are compiled for: odd and even image sizes
+    (partial 2x2 blocks at the right / bottom edge), heavy ties, a NaN/Inf
+    plane (per-pixel general path), and the small 3x3 elements"""
+    monkeypatch.setenv("MORSI_MEDIAN_QUAD", quad)
+    o = oracle()
+    for (h, w) in [(151, 203), (64, 130), (37, 66)]:
+        x = np.stack([M.synth_host(w, h, plane=p, seed=51, dist=p) for p in range(3)])
+        x[x == 0] = 0.0
+        for name in ["disk2.5", "disk3", "disk3.5", "disk4", "disk4.2", "disk5", "cross", "square"]:
+            e = o.element(name)
+            assert_same(M.apply("median", e, x), o.apply("median", e, x), f"{name} median {w}x{h} quad={quad}")
+
+
 def test_all_nan_windows_and_constant_images():
     """windows with no usable neighbour give +-INF (src/morsi.c:63,77), also on the fast paths"""
     o = oracle()
