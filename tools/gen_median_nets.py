@@ -11,7 +11,10 @@ be the median of any of the four windows ("forgetful selection"): the CORE is
 sorted once (Batcher's odd-even merge sort, only the KEEP middle outputs are
 live, the compiler removes the rest), and each pixel merges its sorted EXT and
 UNI samples and selects rank |EXT|+|UNI| of KEEP + EXT + UNI values with
-min_i max(A[i], C[n-1-i]).
+min_i max(A[i], C[n-1-i]).  FULL is a sorting network for all N samples: windows
+with missing or non-finite samples (image border, NaN/Inf data) sort their
+samples with the absent ones replaced by +INF and pick the reference's
+variable-count positions (src/morsi.c:91-101) from the sorted order.
 
     python tools/gen_median_nets.py          # rewrites the header
     python tools/gen_median_nets.py --check  # self-test of the networks only
@@ -85,6 +88,7 @@ def plan(R, hw):
     order = odd_even_merge(list(range(ne)), list(range(ne, ne + nu)), mcomps)
     return dict(N=N, h=h, core=core, ext=ext, uni=uni, drop=drop, keep=keep,
                 core_net=batcher_sort(len(core)), ext_net=batcher_sort(ne), uni_net=batcher_sort(nu),
+                full_net=batcher_sort(N),
                 mrg_net=mcomps, mrg_order=order, D=D)
 
 
@@ -144,14 +148,14 @@ def emit():
         out.append(f"\ntemplate <> struct MedNet<{sid}> {{\n\tstatic constexpr bool ok = true;\n")
         out.append(f"\tstatic constexpr int N = {P['N']}, NCORE = {nc}, NEXT = {ne}, NUNI = {nu}, DROP = {P['drop']}, KEEP = {P['keep']};\n")
         out.append(f"\tstatic constexpr int NCORE_NET = {len(P['core_net'])}, NEXT_NET = {len(P['ext_net'])}, "
-                   f"NUNI_NET = {len(P['uni_net'])}, NMRG_NET = {len(P['mrg_net'])};\n")
+                   f"NUNI_NET = {len(P['uni_net'])}, NMRG_NET = {len(P['mrg_net'])}, NFULL_NET = {len(P['full_net'])};\n")
         out.append(c_array("core_dx", "signed char", [t[0] for t in P["core"]], f"[{nc}]"))
         out.append(c_array("core_dy", "signed char", [t[1] for t in P["core"]], f"[{nc}]"))
         out.append(c_array("ext_dx", "signed char", [t[0] for b in (0, 1) for t in P["ext"][b]], f"[{2 * ne}]"))
         out.append(c_array("ext_dy", "signed char", [t[1] for b in (0, 1) for t in P["ext"][b]], f"[{2 * ne}]"))
         out.append(c_array("uni_dx", "signed char", [t[0] for q in range(4) for t in P["uni"][q]], f"[{4 * nu}]"))
         out.append(c_array("uni_dy", "signed char", [t[1] for q in range(4) for t in P["uni"][q]], f"[{4 * nu}]"))
-        for nm in ("core_net", "ext_net", "uni_net", "mrg_net"):
+        for nm in ("core_net", "ext_net", "uni_net", "mrg_net", "full_net"):
             net = P[nm] or [(0, 0)]
             out.append(c_array(nm + "_a", "unsigned char", [c[0] for c in net], f"[{len(net)}]"))
             out.append(c_array(nm + "_b", "unsigned char", [c[1] for c in net], f"[{len(net)}]"))
