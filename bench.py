@@ -51,43 +51,66 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks under the benchmark's load (B200_PROFILING.md recipe).
+    nvidia-smi needs ~100 ms to start and samples every 20 ms, while a timed
+    region can be a few milliseconds: the sampler is started before the
+    warm-up, and the caller keeps the SAME load running (untimed) after the
+    timed region until a few samples have fallen inside the load window."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
         self.proc = None
+        self.lines = []
+        self.t_load0 = self.t_load1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
 
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line))
+
+    def load_begin(self):
+        self.t_load0 = time.time()
+
+    def samples_under_load(self):
+        return sum(1 for t, _ in self.lines if self.t_load0 is not None and t >= self.t_load0 + 0.002)
+
     def stop(self):
+        self.t_load1 = time.time()
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
         self.proc.terminate()
-        out = self.proc.communicate()[0]
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
         sm, mx, reasons = [], [], set()
-        for line in out.splitlines():
-            f = [t.strip() for t in line.split(",")]
-            if len(f) < 9:
+        for t, line in list(self.lines):
+            if self.t_load0 is None or t < self.t_load0 + 0.002 or t > self.t_load1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm.append(float(f[2])); mx.append(float(f[3]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons),
+                "window": "timed region + the same load continued untimed until >= 5 samples"}
 
 
 def dist_setup(n_gpus):
@@ -227,11 +250,12 @@ def main_ours(args):
     for x in ev:
         check(L.morsi_cuda_event_create(M.binding.ctypes.byref(x)))
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.load_begin()
     L.morsi_cuda_launch_count_reset()
     check(L.morsi_cuda_event_record(ev[0], stream))
     for _ in range(args.steps):
@@ -242,7 +266,6 @@ def main_ours(args):
     ms = M.binding.ctypes.c_float()
     check(L.morsi_cuda_event_elapsed_ms(ev[0], ev[1], M.binding.ctypes.byref(ms)))
     barrier()
-    clocks = sampler.stop()
     elapsed_ms = ms.value
     if dist is not None:
         t = torch.tensor([elapsed_ms], device="cuda")
@@ -253,6 +276,20 @@ def main_ours(args):
         launches = int(lt.item())
     ms_per_step = elapsed_ms / args.steps
     value = samples_per_step_total / (ms_per_step * 1e-3) / 1e6
+    # keep the same load running (untimed) until the clock sampler has seen it;
+    # under torchrun every rank runs the same number of extra steps (a step may
+    # exchange halo rows with its neighbours)
+    if dist is not None:
+        for _ in range(min(5000, int(200.0 / max(ms_per_step, 1e-3)) + 1)):
+            step()
+    else:
+        t_more = time.time()
+        while sampler.proc and sampler.samples_under_load() < 5 and time.time() - t_more < 1.5:
+            for _ in range(max(1, args.steps // 4)):
+                step()
+            check(L.morsi_cuda_sync(stream))
+    barrier()
+    clocks = sampler.stop()
 
     # ---- e2e: the public host-pointer call, pinned host buffers ----------
     e2e = None

@@ -196,9 +196,14 @@ struct DiskCfg {
 		return best;
 	}
 	static constexpr int GP = group_pairs();          // row pairs per group
-	static constexpr int NG = 2;                      // groups per ring (double buffer)
 	static constexpr int PAIR = 2 * RP;               // floats per row pair
 	static constexpr int GROUP = GP * PAIR;           // floats per group
+	// groups per ring: two, or more when the groups are small (a prime period
+	// leaves groups of one pair: keep ~20 KB in flight all the same)
+#ifndef DISK_RING_BYTES
+#define DISK_RING_BYTES (20 * 1024)
+#endif
+	static constexpr int NG = DISK_RING_BYTES / (GROUP * 4) < 2 ? 2 : (DISK_RING_BYTES / (GROUP * 4) > 8 ? 8 : DISK_RING_BYTES / (GROUP * 4));
 	static constexpr unsigned GROUP_BYTES = GROUP * 4u;
 	static constexpr int NACC = 2 * R + 2;            // accumulator slots per column
 	static constexpr int THREADS = TWO ? 2 * NT : NT;
@@ -211,7 +216,11 @@ struct DiskCfg {
 #ifndef DISK_REGS_C2
 #define DISK_REGS_C2 84
 #endif
-	static constexpr int REGS = (C * (2 * R + 2) > 64) ? 255 : (C == 2 ? (C * (2 * R + 2) > 36 ? 128 : DISK_REGS_C2) : DISK_REGS_SMALL);
+#ifndef DISK_REGS_SMALL_W4
+#define DISK_REGS_SMALL_W4 128
+#endif
+	static constexpr int REGS = (C * (2 * R + 2) > 64) ? 255 : (C == 2 ? (C * (2 * R + 2) > 36 ? 128 : DISK_REGS_C2) :
+		(THREADS >= 256 ? DISK_REGS_SMALL_W4 : DISK_REGS_SMALL));
 	static constexpr int MINB = 65536 / (REGS * THREADS) > 0 ? 65536 / (REGS * THREADS) : 1;
 };
 
@@ -685,7 +694,11 @@ static int disk_run(MorsiCtx *c, const DiskArgs &a, int planes, cudaStream_t st)
 	const double c2 = disk_plan<S, C, 2, ISMAX, TWO, HASX>(c, a, planes, &rows2);
 	const double c4 = disk_plan<S, C, 4, ISMAX, TWO, HASX>(c, a, planes, &rows4);
 	const int force = disk_forced_w();
-	if (force == 2 || (force != 4 && c2 < c4))
+	// measured on B200 (C2, disk7): the 4-warp-per-stage CTA never beats the 2-warp one
+	// for the small disks even when the model calls it even; the big disks (255
+	// registers, one CTA per SM either way) prefer 4 (C4: 8.5 ms vs 10.3 ms)
+	const bool small = DiskCfg<S, C, 2, TWO>::REGS < 255;
+	if (force == 2 || (force != 4 && c2 < c4 * (small ? 1.3 : 1.0)))
 		return disk_launch<S, C, 2, ISMAX, TWO, HASX>(c, a, planes, rows2, st);
 	return disk_launch<S, C, 4, ISMAX, TWO, HASX>(c, a, planes, rows4, st);
 }
