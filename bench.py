@@ -355,6 +355,17 @@ def main_ours(args):
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_sample": 8,
                 "note": "per-operation duration = step time / ops per step (CUDA events on the launching stream)"}
+    # The disk and median kernels are bound by the ALU pipe, not by HBM:
+    # min/max instructions per sample (counted in the SASS of the kernel that runs)
+    # against the measured FMNMX/FMNMX3 rate of 64 lanes per clock per SM.
+    minmax_per_sample = {"c2": 2 * 12.8, "c4": 2 * 27.0, "c3": 333.0}.get(name)
+    if minmax_per_sample:
+        sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        alu_peak = 64.0 * 148 * sm_hz
+        alu_ach = minmax_per_sample * per_gpu_samples_per_op / (op_ms * 1e-3)
+        roofline["alu_pipe"] = {"achieved": alu_ach / 1e12, "peak": alu_peak / 1e12, "unit": "T min/max lane-instr/s",
+                                "frac": alu_ach / alu_peak, "minmax_instr_per_sample": minmax_per_sample,
+                                "peak_source": "scratch/ubench_alu.cu: FMNMX3 64 lanes/clk/SM x 148 SMs x SM clock"}
     tr = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tr):
         try:

@@ -7,6 +7,7 @@
 
 #include "dispatch.cuh"
 #include "k_exact.cuh"
+#include "k_tiled.cuh"
 
 OpPlan morsi_op_plan(int op)
 {
@@ -68,6 +69,49 @@ static void launch_exact_t(const ExactArgs &a, int planes, cudaStream_t s)
 	morsi_count_launch(1);
 }
 
+// the tiled kernels for arbitrary lists (k_tiled.cuh); tg == nullptr: the exact ones
+struct TiledLaunch {
+	TiledGeom g;
+	int *flag;
+	size_t smem;
+};
+
+template <int EPI>
+static int launch_tiled_t(const ExactArgs &a, const TiledLaunch &t, int planes, cudaStream_t s)
+{
+	static bool attr_set = false;                  // opt in to > 48 KB of dynamic shared memory once
+	if (!attr_set) {
+		cudaFuncSetAttribute(k_tiled_minmax<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+		attr_set = true;
+	}
+	const int rows_y = (a.y_rows + TILED_TY - 1) / TILED_TY;
+	for (int r0 = 0; r0 < rows_y; r0 += 65535) {   // gridDim.y limit
+		ExactArgs sub = a;
+		const int nb = rows_y - r0 < 65535 ? rows_y - r0 : 65535;
+		sub.y_row0 = a.y_row0 + r0 * TILED_TY;
+		sub.y_rows = a.y_rows - r0 * TILED_TY < nb * TILED_TY ? a.y_rows - r0 * TILED_TY : nb * TILED_TY;
+		sub.y = a.y + (long long)r0 * TILED_TY * a.w;
+		if (a.y2) sub.y2 = a.y2 + (long long)r0 * TILED_TY * a.w;
+		dim3 grid((a.w + TILED_TX - 1) / TILED_TX, nb, planes);
+		k_tiled_minmax<EPI><<<grid, dim3(32, 8), t.smem, s>>>(sub, t.g, t.flag);
+		morsi_count_launch(1);
+	}
+	MORSI_CU(cudaGetLastError());
+	return MORSI_OK;
+}
+
+static int launch_tiled(int epi, const ExactArgs &a, const TiledLaunch &t, int planes, cudaStream_t s)
+{
+	switch (epi) {
+#define C(E) case E: return launch_tiled_t<E>(a, t, planes, s);
+	C(EPI_A) C(EPI_B) C(EPI_B_SUB_A) C(EPI_X_SUB_A) C(EPI_B_SUB_X) C(EPI_LAP) C(EPI_ENH)
+	C(EPI_BLUR) C(EPI_A_SUB_B) C(EPI_X_SUB_B) C(EPI_A_SUB_X) C(EPI_IBLUR) C(EPI_EBLUR)
+	C(EPI_CBLUR) C(EPI_AB)
+#undef C
+	}
+	return morsi_set_error(MORSI_ERR_INVALID, "bad epilogue %d", epi);
+}
+
 static int launch_exact(int epi, const ExactArgs &a, int planes, cudaStream_t s)
 {
 	switch (epi) {
@@ -85,7 +129,15 @@ static int launch_exact(int epi, const ExactArgs &a, int planes, cudaStream_t s)
 // The order-preserving path for every operation: one or two passes of
 // k_exact_minmax, temporaries in the context workspace.  `gate` (device word)
 // makes every kernel a no-op unless it is non-zero.
+static int run_minmax_passes(MorsiCtx *c, const DevElement *de, const MorsiJob &job, const int *gate, const TiledLaunch *tl);
+
 int morsi_run_exact(MorsiCtx *c, const DevElement *de, const MorsiJob &job, const int *gate)
+{
+	return run_minmax_passes(c, de, job, gate, nullptr);
+}
+
+// tl == nullptr: k_exact_* (order preserving); else k_tiled_minmax (min/max operations only)
+static int run_minmax_passes(MorsiCtx *c, const DevElement *de, const MorsiJob &job, const int *gate, const TiledLaunch *tl)
 {
 	const OpPlan plan = morsi_op_plan(job.op);
 	const int w = job.w, h = job.h;
@@ -129,18 +181,26 @@ int morsi_run_exact(MorsiCtx *c, const DevElement *de, const MorsiJob &job, cons
 			tmin = Band{(float *)p0, t0, tps}; tmax = Band{(float *)p1, t0, tps}; }
 		else if (plan.t_min) { s1.y = (float *)p0; epi1 = EPI_A; tmin = Band{(float *)p0, t0, tps}; }
 		else { s1.y = (float *)p0; epi1 = EPI_B; tmax = Band{(float *)p0, t0, tps}; }
-		rc = launch_exact(epi1, s1, job.planes, job.stream);
+		if (tl) { TiledLaunch t1 = *tl; t1.g.two_tiles = 0; rc = launch_tiled(epi1, s1, t1, job.planes, job.stream); }
+		else rc = launch_exact(epi1, s1, job.planes, job.stream);
 		if (rc) return rc;
 	}
 	const Band *srcs[4] = {&xb, &xb, &tmin, &tmax};
 	a.a_src = *srcs[plan.a_from]; a.b_src = *srcs[plan.b_from];
 	a.y = job.y; a.y_pstride = job.y_pstride; a.y_row0 = job.y_row0; a.y_rows = job.y_rows;
+	if (tl) {
+		TiledLaunch t2 = *tl;
+		t2.g.two_tiles = plan.a_from && plan.b_from && a.a_src.p != a.b_src.p;
+		if (t2.g.two_tiles) t2.smem += (size_t)t2.g.pw * t2.g.ph * sizeof(float);
+		if (t2.smem > 200 * 1024) return morsi_set_error(MORSI_ERR_INVALID, "tiled: element too large for two tiles");
+		return launch_tiled(plan.epi, a, t2, job.planes, job.stream);
+	}
 	return launch_exact(plan.epi, a, job.planes, job.stream);
 }
 
 // Exact path with bounded temporaries: the job is cut into plane groups and
 // row chunks so that a two-stage temporary never exceeds ~256 MiB per slot.
-static int run_exact_chunked(MorsiCtx *c, const DevElement *de, const MorsiJob &job, const int *gate)
+static int run_exact_chunked(MorsiCtx *c, const DevElement *de, const MorsiJob &job, const int *gate, const TiledLaunch *tl = nullptr)
 {
 	const OpPlan plan = morsi_op_plan(job.op);
 	const long long budget = 256LL << 20;
@@ -165,9 +225,34 @@ static int run_exact_chunked(MorsiCtx *c, const DevElement *de, const MorsiJob &
 			sub.y = job.y + p0 * job.y_pstride + (long long)r0 * job.w;
 			sub.y_row0 = job.y_row0 + r0;
 			sub.y_rows = job.y_rows - r0 < rows_per ? job.y_rows - r0 : rows_per;
-			int rc = morsi_run_exact(c, de, sub, gate);
+			int rc = run_minmax_passes(c, de, sub, gate, tl);
 			if (rc) return rc;
 		}
+	return MORSI_OK;
+}
+
+// Arbitrary lists the specialised families left: evaluate from shared-memory tiles.
+int morsi_run_tiled(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled)
+{
+	*handled = 0;
+	const OpPlan plan = morsi_op_plan(job.op);
+	if (plan.special || de->n < 1 || de->n > 8192 || !de->d_tile_offs) return MORSI_OK;
+	static const bool off = getenv("MORSI_TILED") && !strcmp(getenv("MORSI_TILED"), "0");
+	if (off) return MORSI_OK;
+	TiledLaunch t;
+	t.g.xmin = de->info.xmin; t.g.xmax = de->info.xmax; t.g.ymin = de->info.ymin; t.g.ymax = de->info.ymax;
+	t.g.pw = TILED_TX + de->info.xmax - de->info.xmin;
+	t.g.ph = TILED_TY + de->info.ymax - de->info.ymin;
+	t.g.tile_offs = de->d_tile_offs;
+	t.g.two_tiles = 0;
+	t.flag = flag;
+	t.smem = (size_t)t.g.pw * t.g.ph * sizeof(float) + (size_t)de->n * sizeof(int);
+	// oscillation's last pass needs two tiles
+	const size_t worst = t.smem + ((plan.t_min && plan.t_max) ? (size_t)t.g.pw * t.g.ph * sizeof(float) : 0);
+	if (worst > 200 * 1024) return MORSI_OK;
+	int rc = run_exact_chunked(c, de, job, nullptr, &t);
+	if (rc) return rc;
+	*handled = 1;
 	return MORSI_OK;
 }
 

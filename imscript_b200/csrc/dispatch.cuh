@@ -9,7 +9,7 @@
 #include "common.cuh"
 #include "element.h"
 
-#define MORSI_WS_SLOTS 6   // 0-3: kernel temporaries, 4-5: host-pipeline staging
+#define MORSI_WS_SLOTS 8   // 0-3: kernel temporaries, 4-5: host-pipeline staging, 6-7: pitched copies (k_disk)
 #define MORSI_LANES 4   // lane 0: the *_device entry points; 1..3: host-pointer pipeline
 
 // compiled form of a row-run element (k_rowrun.cu)
@@ -22,6 +22,7 @@ struct RowRunPlan {
 struct DevElement {
 	int n;
 	int2 *d_offs;                 // effective offsets, element order, on the device
+	int *d_tile_offs;             // k_tiled: (dy-ymin)*pw + (dx-xmin) per element, pw = 128 + xmax - xmin
 	morsi_element_info info;
 	RowRunPlan rowrun;
 };
@@ -47,6 +48,7 @@ struct MorsiJob {
 	float *y;       int y_row0, y_rows; long long y_pstride;
 	cudaStream_t stream;
 	int lane;          // workspace / flag lane
+	int pitch = 0;     // floats between rows of x and y; 0: w (only k_disk's pitched copies use another)
 };
 
 // how an operation decomposes into min/max passes (src/morsi.c:141-275)

@@ -56,6 +56,7 @@ struct DiskArgs {
 	int y_row0, y_rows;
 	int src_rows;      // rows held by src (for the loader's bounds)
 	int w, h;
+	int pitch;         // floats between rows of every operand (>= w, multiple of 4)
 	int band_rows;     // output rows per CTA
 	int epi;
 	int *flag;
@@ -394,6 +395,7 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 	const int nout = min(p.band_rows, p.y_rows - o_base);
 	const int Y0 = p.y_row0 + o_base;                 // global row of relative output 0
 	const int w = p.w, h = p.h;
+	const long long pitch = p.pitch;
 	const int G2 = (nout + 2 * R + 1) / 2;            // row pairs of the final reduction
 	const int Gin = TWO ? G2 + R : G2;                // row pairs of the input ring
 	const int Gmine = first ? Gin : G2;
@@ -452,10 +454,11 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 	// final stage: output columns
 	const int x = cx0 + C * mt;
 	const bool col_ok = !first && x < w && C * mt < K::OUTW;
+	const bool pad_edge = !TWO && col_ok && x + C > w;              // the thread that straddles the true width
 	// running pointers to output row 2g-2R of this thread's columns
-	float *yq = p.y + plane * p.y_pstride + (long long)(Y0 - p.y_row0 - 2 * R) * w + x;
-	const float *xq = p.xop.p ? p.xop.p + plane * p.xop.pstride + (long long)(Y0 - p.xop.row0 - 2 * R) * w + x : nullptr;
-	const float *oq = (!TWO && p.other.p) ? p.other.p + plane * p.other.pstride + (long long)(Y0 - p.other.row0 - 2 * R) * w + x : nullptr;
+	float *yq = p.y + plane * p.y_pstride + (long long)(Y0 - p.y_row0 - 2 * R) * pitch + x;
+	const float *xq = p.xop.p ? p.xop.p + plane * p.xop.pstride + (long long)(Y0 - p.xop.row0 - 2 * R) * pitch + x : nullptr;
+	const float *oq = (!TWO && p.other.p) ? p.other.p + plane * p.other.pstride + (long long)(Y0 - p.other.row0 - 2 * R) * pitch + x : nullptr;
 	const int epi = p.epi;
 	const bool plain = epi == (ISMAX ? EPI_B : EPI_A);                 // single stage only
 	int gi = 0;                                                        // group being consumed
@@ -489,7 +492,7 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 				float xv0[C], xv1[C];
 				if (TWO && HASX) {
 					if (e0) load_cols<C>(xq, xv0);
-					if (e1) load_cols<C>(xq + w, xv1);
+					if (e1) load_cols<C>(xq + pitch, xv1);
 				}
 				D::step(acc, hs, s % (R + 1), rowA, rowA + RP, zmin, reads_input,
 					// the group has been read (its loads were issued before this
@@ -539,7 +542,7 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 #pragma unroll
 							for (int c = 0; c < C; c++)
 								v[c] = !HASX ? -m1[c] : ISMAX ? __fsub_rn(-m1[c], xv1[c]) : __fsub_rn(xv1[c], -m1[c]);
-							store_cols<C>(yq + w, v);
+							store_cols<C>(yq + pitch, v);
 						}
 					} else {
 						if (e0) {
@@ -547,15 +550,25 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 							else disk_emit_general<ISMAX>(yq, xq, oq, epi, C, m0[0], m0[1], C == 4 ? m0[2] : 0.f, C == 4 ? m0[3] : 0.f);
 						}
 						if (e1) {
-							if (plain) store_cols<C>(yq + w, m1);
-							else disk_emit_general<ISMAX>(yq + w, xq ? xq + w : nullptr, oq ? oq + w : nullptr,
+							if (plain) store_cols<C>(yq + pitch, m1);
+							else disk_emit_general<ISMAX>(yq + pitch, xq ? xq + pitch : nullptr, oq ? oq + pitch : nullptr,
 									epi, C, m1[0], m1[1], C == 4 ? m1[2] : 0.f, C == 4 ? m1[3] : 0.f);
+						}
+						// pitched copies (w % 4 != 0): the pad columns of a row stay NaN, the
+						// result may be the source of a later pass (oscillation)
+						if (pad_edge) {
+#pragma unroll
+							for (int c = 0; c < C; c++)
+								if (x + c >= w) {
+									if (e0) yq[c] = CUDART_NAN_F;
+									if (e1) yq[pitch + c] = CUDART_NAN_F;
+								}
 						}
 					}
 				});
-				yq += 2 * w;
-				if ((TWO && HASX) || !TWO) { if (xq) xq += 2 * w; }
-				if (!TWO) { if (oq) oq += 2 * w; }
+				yq += 2 * pitch;
+				if ((TWO && HASX) || !TWO) { if (xq) xq += 2 * pitch; }
+				if (!TWO) { if (oq) oq += 2 * pitch; }
 			}
 		}
 	}
@@ -636,7 +649,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 		const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
 		CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int disk_tensor_map(CUtensorMap *tm, const Band &src, int src_rows, int w, int planes, int rp, int nrows, int *bw_out)
+static int disk_tensor_map(CUtensorMap *tm, const Band &src, int src_rows, int w /* = the row pitch */, int planes, int rp, int nrows, int *bw_out)
 {
 	static EncodeTiledFn encode = nullptr;
 	if (!encode) {
@@ -670,7 +683,8 @@ static int disk_launch(const MorsiCtx *c, const DiskArgs &a0, int planes, int ba
 	a.band_rows = band_rows;
 	CUtensorMap tm;
 	int bw = 4;
-	int rc = disk_tensor_map(&tm, a.src, a.src_rows, a.w, planes, K::RP, 2 * K::GP, &bw);
+	// over the row PITCH: pad columns [w, pitch) hold NaN (absent, like everything outside)
+	int rc = disk_tensor_map(&tm, a.src, a.src_rows, a.pitch, planes, K::RP, 2 * K::GP, &bw);
 	if (rc) return rc;
 	const int strips = (a.w + K::OUTW - 1) / K::OUTW;
 	dim3 grid(strips, (a.y_rows + band_rows - 1) / band_rows, planes);
@@ -767,19 +781,16 @@ static int disk_pass(MorsiCtx *c, int id, bool ismax, int epi, const MorsiJob &j
 	a.src = src; a.src_rows = src_rows; a.xop = xop; a.other = other;
 	a.y = dst; a.y_pstride = dst_pstride; a.y_row0 = row0; a.y_rows = rows;
 	a.w = job.w; a.h = job.h; a.epi = epi; a.flag = flag; a.band_rows = rows;
+	a.pitch = job.pitch ? job.pitch : job.w;
 	return launch_by_id(id, c, a, job.planes, ismax, false, job.stream);
 }
 
-int morsi_run_disk(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled)
+// The passes of one operation over operands whose rows are P = job.pitch (or
+// job.w) floats apart, 16-byte aligned.
+static int run_disk_passes(MorsiCtx *c, int id, const DevElement *de, const MorsiJob &job, int *flag)
 {
-	*handled = 0;
 	const OpPlan plan = morsi_op_plan(job.op);
-	if (plan.special) return MORSI_OK;
-	const int id = find_shape(de->rowrun);
-	if (id < 0) return MORSI_OK;
-	const bool aligned = (job.w % 4 == 0) && (((uintptr_t)job.x) % 16 == 0) && (((uintptr_t)job.y) % 16 == 0)
-		&& (job.x_pstride % 4 == 0) && (job.y_pstride % 4 == 0);
-	if (!aligned) return MORSI_OK;
+	const int P = job.pitch ? job.pitch : job.w;
 	const int R = de->rowrun.reach;
 	const Band none{nullptr, 0, 0};
 	const Band xb{job.x, job.x_row0, job.x_pstride};
@@ -795,9 +806,7 @@ int morsi_run_disk(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *
 	if (plan.stages == 1 && !both1) {
 		rc = disk_pass(c, id, plan.b_from != 0, plan.epi, job, xb, job.x_rows, xb, none,
 				job.y, job.y_pstride, job.y_row0, job.y_rows, flag);
-		if (rc) return rc;
-		*handled = 1;
-		return MORSI_OK;
+		return rc;
 	}
 	if (plan.stages == 2 && !osc) {
 		// opening, closing, tophat, bothat: both stages in one kernel
@@ -806,24 +815,22 @@ int morsi_run_disk(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *
 		a.xop = (plan.epi == EPI_X_SUB_B || plan.epi == EPI_A_SUB_X) ? xb : none;
 		a.y = job.y; a.y_pstride = job.y_pstride; a.y_row0 = job.y_row0; a.y_rows = job.y_rows;
 		a.w = job.w; a.h = job.h; a.epi = plan.epi; a.flag = flag; a.band_rows = job.y_rows;
-		rc = launch_by_id(id, c, a, job.planes, plan.t_max != 0, true, job.stream);
-		if (rc) return rc;
-		*handled = 1;
-		return MORSI_OK;
+		a.pitch = P;
+		return launch_by_id(id, c, a, job.planes, plan.t_max != 0, true, job.stream);
 	}
 	// temporaries cover the output band grown by one reach (clipped); chunk the
 	// band so that a temporary stays below 512 MiB
 	const long long budget = 512LL << 20;
-	long long rows_fit = budget / ((long long)job.w * 4 * job.planes) - 2 * R;
+	long long rows_fit = budget / ((long long)P * 4 * job.planes) - 2 * R;
 	if (rows_fit < 8 * R + 64) rows_fit = 8 * R + 64;
 	const int chunk = (int)(rows_fit < job.y_rows ? rows_fit : job.y_rows);
 	for (int r0 = 0; r0 < job.y_rows; r0 += chunk) {
 		const int o0 = job.y_row0 + r0;
 		const int orows = job.y_rows - r0 < chunk ? job.y_rows - r0 : chunk;
-		float *ydst = job.y + (long long)r0 * job.w;
+		float *ydst = job.y + (long long)r0 * P;
 		if (both1) {
-			void *p0; if ((rc = morsi_ws_get(c, job.lane, 0, (size_t)job.w * orows * job.planes * 4, &p0))) return rc;
-			const long long tps = (long long)job.w * orows;
+			void *p0; if ((rc = morsi_ws_get(c, job.lane, 0, (size_t)P * orows * job.planes * 4, &p0))) return rc;
+			const long long tps = (long long)P * orows;
 			rc = disk_pass(c, id, false, EPI_A, job, xb, job.x_rows, none, none, (float *)p0, tps, o0, orows, flag);
 			if (rc) return rc;
 			rc = disk_pass(c, id, true, plan.epi, job, xb, job.x_rows, xb, Band{(float *)p0, o0, tps},
@@ -836,13 +843,13 @@ int morsi_run_disk(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *
 		int t0 = o0 - R; if (t0 < 0) t0 = 0;
 		int t1 = o0 + orows + R; if (t1 > job.h) t1 = job.h;
 		const int trows = t1 - t0;
-		const long long tps = (long long)job.w * trows;
+		const long long tps = (long long)P * trows;
 		const size_t tbytes = (size_t)tps * job.planes * 4;
 		void *p0, *p1, *p2;
 		if ((rc = morsi_ws_get(c, job.lane, 0, tbytes, &p0))) return rc;
 		if ((rc = morsi_ws_get(c, job.lane, 1, tbytes, &p1))) return rc;
-		if ((rc = morsi_ws_get(c, job.lane, 2, (size_t)job.w * orows * job.planes * 4, &p2))) return rc;
-		const long long ops = (long long)job.w * orows;
+		if ((rc = morsi_ws_get(c, job.lane, 2, (size_t)P * orows * job.planes * 4, &p2))) return rc;
+		const long long ops = (long long)P * orows;
 		rc = disk_pass(c, id, false, EPI_A, job, xb, job.x_rows, none, none, (float *)p0, tps, t0, trows, flag);
 		if (rc) return rc;
 		rc = disk_pass(c, id, true, EPI_B, job, xb, job.x_rows, none, none, (float *)p1, tps, t0, trows, flag);
@@ -853,6 +860,87 @@ int morsi_run_disk(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *
 		rc = disk_pass(c, id, false, EPI_A_SUB_B, job, Band{(float *)p1, t0, tps}, trows, none,
 				Band{(float *)p2, o0, ops}, ydst, job.y_pstride, o0, orows, flag);
 		if (rc) return rc;
+	}
+	return MORSI_OK;
+}
+
+// ---- widths / bases the TMA path cannot address directly -------------------------------
+// Rows of a caller's plane are w floats apart; a tensor map needs a 16-byte
+// pitch and base.  Such jobs run on pitched copies in the workspace: the copy
+// in pads every row to a multiple of 4 floats with NaN (absent samples, like
+// everything outside the image; the kernels still mask their temporaries with
+// the true w), the copy out drops the pad.  16 B/sample of extra HBM traffic on
+// kernels that are bound by the ALU pipe, instead of the exact kernels' n
+// gathers per sample.
+__global__ void __launch_bounds__(256) k_pitch_in(const float *x, long long x_pstride, float *d, long long d_pstride,
+		int w, int pitch, int rows)
+{
+	const int plane = blockIdx.z;
+	const int i = blockIdx.x * 256 + threadIdx.x;
+	if (i >= pitch) return;
+	for (int r = blockIdx.y; r < rows; r += gridDim.y)
+		d[plane * d_pstride + (long long)r * pitch + i] = i < w ? __ldg(x + plane * x_pstride + (long long)r * w + i) : CUDART_NAN_F;
+}
+__global__ void __launch_bounds__(256) k_pitch_out(const float *s, long long s_pstride, float *y, long long y_pstride,
+		int w, int pitch, int rows)
+{
+	const int plane = blockIdx.z;
+	const int i = blockIdx.x * 256 + threadIdx.x;
+	if (i >= w) return;
+	for (int r = blockIdx.y; r < rows; r += gridDim.y)
+		y[plane * y_pstride + (long long)r * w + i] = s[plane * s_pstride + (long long)r * pitch + i];
+}
+
+int morsi_run_disk(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled)
+{
+	*handled = 0;
+	const OpPlan plan = morsi_op_plan(job.op);
+	if (plan.special) return MORSI_OK;
+	const int id = find_shape(de->rowrun);
+	if (id < 0) return MORSI_OK;
+	const bool aligned = (job.w % 4 == 0) && (((uintptr_t)job.x) % 16 == 0) && (((uintptr_t)job.y) % 16 == 0)
+		&& (job.x_pstride % 4 == 0) && (job.y_pstride % 4 == 0);
+	int rc;
+	if (aligned) {
+		rc = run_disk_passes(c, id, de, job, flag);
+		if (rc) return rc;
+		*handled = 1;
+		return MORSI_OK;
+	}
+	if (job.planes > 65535) return MORSI_OK;
+	// pitched copies, in row chunks of at most ~256 MiB per copy
+	const int R = de->rowrun.reach;
+	const int halo = R * plan.stages;
+	const int P = (job.w + 3) & ~3;
+	long long rows_fit = (256LL << 20) / ((long long)P * 4 * job.planes) - 2 * halo;
+	if (rows_fit < 8 * halo + 64) rows_fit = 8 * halo + 64;
+	const int chunk = (int)(rows_fit < job.y_rows ? rows_fit : job.y_rows);
+	for (int r0 = 0; r0 < job.y_rows; r0 += chunk) {
+		const int o0 = job.y_row0 + r0;
+		const int orows = job.y_rows - r0 < chunk ? job.y_rows - r0 : chunk;
+		// input rows the chunk needs, clipped to what the caller's band holds
+		int i0 = o0 - halo, i1 = o0 + orows + halo;
+		if (i0 < job.x_row0) i0 = job.x_row0;
+		if (i1 > job.x_row0 + job.x_rows) i1 = job.x_row0 + job.x_rows;
+		const int irows = i1 - i0;
+		void *px, *py;
+		if ((rc = morsi_ws_get(c, job.lane, 6, (size_t)P * irows * job.planes * 4, &px))) return rc;
+		if ((rc = morsi_ws_get(c, job.lane, 7, (size_t)P * orows * job.planes * 4, &py))) return rc;
+		const dim3 gi((P + 255) / 256, irows < 1024 ? irows : 1024, job.planes);
+		k_pitch_in<<<gi, 256, 0, job.stream>>>(job.x + (long long)(i0 - job.x_row0) * job.w, job.x_pstride,
+				(float *)px, (long long)P * irows, job.w, P, irows);
+		morsi_count_launch(1);
+		MORSI_CU(cudaGetLastError());
+		MorsiJob sub = job;
+		sub.pitch = P;
+		sub.x = (const float *)px; sub.x_row0 = i0; sub.x_rows = irows; sub.x_pstride = (long long)P * irows;
+		sub.y = (float *)py; sub.y_row0 = o0; sub.y_rows = orows; sub.y_pstride = (long long)P * orows;
+		if ((rc = run_disk_passes(c, id, de, sub, flag))) return rc;
+		const dim3 go((job.w + 255) / 256, orows < 1024 ? orows : 1024, job.planes);
+		k_pitch_out<<<go, 256, 0, job.stream>>>((const float *)py, (long long)P * orows,
+				job.y + (long long)r0 * job.w, job.y_pstride, job.w, P, orows);
+		morsi_count_launch(1);
+		MORSI_CU(cudaGetLastError());
 	}
 	*handled = 1;
 	return MORSI_OK;

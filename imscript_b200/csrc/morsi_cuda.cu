@@ -158,7 +158,7 @@ extern "C" void morsi_cuda_shutdown(void)
 		MorsiCtx *c = kv.second;
 		cudaSetDevice(c->device);
 		cudaStreamSynchronize(c->stream);
-		for (auto &e : c->elements) cudaFree(e.second.d_offs);
+		for (auto &e : c->elements) { cudaFree(e.second.d_offs); cudaFree(e.second.d_tile_offs); }
 		for (int l = 0; l < MORSI_LANES; l++)
 			for (int i = 0; i < MORSI_WS_SLOTS; i++) cudaFree(c->ws[l][i]);
 		for (int l = 0; l < MORSI_LANES; l++) if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
@@ -203,6 +203,16 @@ int morsi_element_get(MorsiCtx *c, const int *e, const DevElement **out)
 		offs[k] = make_int2(e[4 + 2*k] - e[2], e[5 + 2*k] - e[3]);
 	CU(cudaMalloc(&d.d_offs, ((size_t)d.n + 1) * sizeof(int2)));
 	CU(cudaMemcpy(d.d_offs, offs.data(), ((size_t)d.n + 1) * sizeof(int2), cudaMemcpyHostToDevice));
+	// k_tiled: offsets into a shared-memory tile of pitch 128 + (xmax - xmin)
+	d.d_tile_offs = nullptr;
+	if (d.n > 0 && d.n <= 8192) {
+		const int pw = 128 + d.info.xmax - d.info.xmin;
+		std::vector<int> toffs((size_t)d.n);
+		for (int k = 0; k < d.n; k++)
+			toffs[k] = (offs[k].y - d.info.ymin) * pw + (offs[k].x - d.info.xmin);
+		CU(cudaMalloc(&d.d_tile_offs, (size_t)d.n * sizeof(int)));
+		CU(cudaMemcpy(d.d_tile_offs, toffs.data(), (size_t)d.n * sizeof(int), cudaMemcpyHostToDevice));
+	}
 	morsi_element_compile(c, &d);
 	auto ins = c->elements.emplace(key, d);
 	*out = &ins.first->second;

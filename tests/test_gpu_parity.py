@@ -104,6 +104,21 @@ def test_disk_kernels_multi_strip_multi_band(warps, monkeypatch):
             assert_same(M.apply(op, e, x), o.apply(op, e, x), f"{name} {op} {w}x{h} W={warps}")
 
 
+def test_disk_kernels_unaligned_width():
+    """widths that are not a multiple of 4 (a TMA tensor map cannot address them):
+    k_disk runs on NaN-padded pitched copies; the pad columns must stay absent for
+    the second pass of oscillation, and the result is bit-identical all the same"""
+    o = oracle()
+    for (h, w) in [(230, 1001), (97, 131), (64, 67), (300, 258)]:
+        x = np.stack([M.synth_host(w, h, plane=p, seed=77, dist=2 if p == 1 else 0) for p in range(2)])
+        x[x == 0] = 0.0                      # no -0.0: the result must come from the fast kernels
+        for name in ("disk4.2", "disk7", "disk15"):
+            e = o.element(name)
+            for op in ("erosion", "dilation", "opening", "closing", "tophat", "bothat", "gradient",
+                       "oscillation", "laplacian", "cblur", "eblur"):
+                assert_same(M.apply(op, e, x), o.apply(op, e, x), f"{name} {op} {w}x{h} unaligned")
+
+
 @pytest.mark.parametrize("quad", ["1", "0"])
 def test_median_fast_kernels(quad, monkeypatch):
     """median by every disk the shared-window kernel (k_median_quad) and the
