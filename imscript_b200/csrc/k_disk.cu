@@ -742,7 +742,7 @@ static int disk_shape(MorsiCtx *c, const DiskArgs &a, int planes, bool ismax, bo
 #ifdef MORSI_DISK_IDS
 #define DISK_IDS MORSI_DISK_IDS
 #else
-#define DISK_IDS T(0) T(1) T(2) T(3) T(4) T(5) T(6) T(7) T(8) T(9) T(10) T(11) T(12) T(13)
+#define DISK_IDS T(0) T(1) T(2) T(3) T(4) T(5) T(6) T(7) T(8) T(9) T(10) T(11) T(12) T(13) T(16) T(17) T(18)
 #endif
 
 template <int ID>

@@ -84,29 +84,43 @@ template <int HALO>
 struct RawRow {
 	float c[4];
 	float e[HALO];      // lane 0: columns x0-1 (, x0-2); lane 31: columns x0+4 (, x0+5)
+	unsigned ok;        // VEC: bit 0: c[] exist, bit 1+k: e[k] exists (absent samples are NaN on use)
 };
 
+// VEC: unconditional loads (absent samples read the plane's first floats
+// instead) so that every prefetch slot keeps its own registers in flight; see
+// fetch1 below for what a predicated load into a NaN-initialised register costs.
 template <int HALO, bool VEC>
 __device__ __forceinline__ void fetch_row(const float *plane, int row0, int w, int h,
 		int j, int x0, int lane, RawRow<HALO> &r)
 {
+	const bool rowok = j >= 0 && j < h;
+	const float *row = plane + (long long)(j - row0) * w;
+	if (VEC) {
+		const bool cok = rowok && x0 < w;
+		const float4 q = __ldg(reinterpret_cast<const float4 *>(cok ? row + x0 : plane));
+		r.c[0] = q.x; r.c[1] = q.y; r.c[2] = q.z; r.c[3] = q.w;
+		unsigned ok = cok ? 1u : 0u;
+#pragma unroll
+		for (int k = 0; k < HALO; k++) {
+			const int off = lane == 0 ? -1 - k : 4 + k;
+			const bool eok = rowok && ((lane == 0 && x0 - 1 - k >= 0 && x0 - 1 - k < w) || (lane == 31 && x0 + 4 + k < w));
+			r.e[k] = __ldg(eok ? row + x0 + off : plane);
+			ok |= eok ? (2u << k) : 0u;
+		}
+		r.ok = ok;
+		return;
+	}
 	const float nan = CUDART_NAN_F;
+	r.ok = ~0u;
 #pragma unroll
 	for (int k = 0; k < 4; k++) r.c[k] = nan;
 #pragma unroll
 	for (int k = 0; k < HALO; k++) r.e[k] = nan;
-	if (j < 0 || j >= h) return;
-	const float *row = plane + (long long)(j - row0) * w;
-	if (VEC) {
-		if (x0 < w) {
-			float4 q = __ldg(reinterpret_cast<const float4 *>(row + x0));
-			r.c[0] = q.x; r.c[1] = q.y; r.c[2] = q.z; r.c[3] = q.w;
-		}
-	} else {
+	if (!rowok) return;
 #pragma unroll
-		for (int k = 0; k < 4; k++)
-			if (x0 + k < w) r.c[k] = __ldg(row + x0 + k);
-	}
+	for (int k = 0; k < 4; k++)
+		if (x0 + k < w) r.c[k] = __ldg(row + x0 + k);
 	if (lane == 0) {
 #pragma unroll
 		for (int k = 0; k < HALO; k++)
@@ -121,9 +135,14 @@ __device__ __forceinline__ void fetch_row(const float *plane, int row0, int w, i
 
 // columns x0-HALO .. x0+3+HALO of a fetched row into v[0 .. 4+2*HALO)
 template <int HALO>
-__device__ __forceinline__ void assemble_row(const RawRow<HALO> &r, int lane,
+__device__ __forceinline__ void assemble_row(const RawRow<HALO> &r0, int lane,
 		float (&v)[4 + 2 * HALO], unsigned &negzero)
 {
+	RawRow<HALO> r = r0;
+	const float nan = CUDART_NAN_F;
+	if (!(r.ok & 1u)) { r.c[0] = nan; r.c[1] = nan; r.c[2] = nan; r.c[3] = nan; }
+#pragma unroll
+	for (int k = 0; k < HALO; k++) if (!(r.ok & (2u << k))) r.e[k] = nan;
 	negzero |= (__float_as_uint(r.c[0]) == 0x80000000u) | (__float_as_uint(r.c[1]) == 0x80000000u) |
 	           (__float_as_uint(r.c[2]) == 0x80000000u) | (__float_as_uint(r.c[3]) == 0x80000000u);
 #pragma unroll

@@ -28,3 +28,7 @@ MORSI_SHAPE(13, 14, 5, 7, 8, 10, 11, 11, 12, 13, 13, 14, 14, 14, 14, 14, 14, 14,
 
 MORSI_SHAPE(14, 1, 0, 1, 0)                                         // cross (as a set; element order differs)
 MORSI_SHAPE(15, 1, 1, 1, 1)                                         // square, disk2
+// more disks (k_disk only)
+MORSI_SHAPE(16, 10, 4, 6, 7, 8, 9, 9, 10, 10, 10, 10, 10, 10, 10, 10, 10, 9, 9, 8, 7, 6, 4)   // disk11
+MORSI_SHAPE(17, 12, 4, 6, 8, 9, 10, 10, 11, 11, 12, 12, 12, 12, 12, 12, 12, 12, 12, 11, 11, 10, 10, 9, 8, 6, 4)   // disk13
+MORSI_SHAPE(18, 13, 5, 7, 8, 9, 10, 11, 12, 12, 13, 13, 13, 13, 13, 13, 13, 13, 13, 13, 13, 12, 12, 11, 10, 9, 8, 7, 5)   // disk14

@@ -76,7 +76,7 @@ def test_vs_oracle_shapes_elements_ops(dist):
 
 
 DISKS = ["disk2.5", "disk3", "disk3.5", "disk4", "disk4.2", "disk5", "disk5.1", "disk6", "disk7", "disk8",
-         "disk9", "disk10", "disk12", "disk15"]
+         "disk9", "disk10", "disk11", "disk12", "disk13", "disk14", "disk15"]
 
 
 @pytest.mark.parametrize("warps", ["2", "4"])
