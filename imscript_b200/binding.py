@@ -15,7 +15,7 @@ EXPORTED_SYMBOLS = [
     "morsi_build_disk", "morsi_build_dysk", "morsi_build_hrec", "morsi_build_vrec",
     "morsi_build_drec", "morsi_build_Drec", "morsi_element_free", "morsi_operation_parse",
     "morsi_operation_name", "morsi_element_describe", "morsi_cuda_device_count",
-    "morsi_cuda_init", "morsi_cuda_shutdown", "morsi_cuda_apply", "morsi_cuda_apply_device",
+    "morsi_cuda_init", "morsi_cuda_shutdown", "morsi_cuda_apply", "morsi_cuda_apply_all", "morsi_cuda_apply_device",
     "morsi_cuda_apply_band_device", "morsi_cuda_halo_rows", "morsi_cuda_set_path",
     "morsi_cuda_launch_count", "morsi_cuda_launch_count_reset", "morsi_cuda_malloc",
     "morsi_cuda_free", "morsi_cuda_host_alloc", "morsi_cuda_host_free", "morsi_cuda_memcpy_h2d",
@@ -68,6 +68,7 @@ def lib():
         L.morsi_element_describe.argtypes = [_i32p, ctypes.c_char_p, ctypes.c_size_t]
         L.morsi_cuda_apply.argtypes = [ctypes.c_int, _i32p, _vp, _vp,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.morsi_cuda_apply_all.argtypes = [_i32p, _vp, ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.morsi_cuda_apply_device.argtypes = [ctypes.c_int, _i32p, _vp, _vp, ctypes.c_int,
                                               ctypes.c_int, ctypes.c_int, _vp]
         L.morsi_cuda_apply_band_device.argtypes = [ctypes.c_int, _i32p, _vp, ctypes.c_int, ctypes.c_int,

@@ -45,20 +45,19 @@ WRAP(cblur, MORSI_CBLUR)
 
 /* src/morsi.c:278-310: every non-NULL output is filled; `o_str` is the
  * oscillation.  Each output equals the single-operation result (the
- * reference's shared temporaries do not change any value). */
+ * reference's shared temporaries do not change any value); the input is
+ * uploaded once (morsi_cuda_apply_all). */
 void morsi_all(float *o_ero, float *o_dil, float *o_ope, float *o_clo,
 		float *o_grad, float *o_igrad, float *o_egrad,
 		float *o_lap, float *o_enh, float *o_str,
 		float *o_top, float *o_bot, float *x, int w, int h, int *e)
 {
-	struct { float *out; int op; } t[12] = {
-		{o_ero, MORSI_EROSION}, {o_dil, MORSI_DILATION}, {o_ope, MORSI_OPENING},
-		{o_clo, MORSI_CLOSING}, {o_grad, MORSI_GRADIENT}, {o_igrad, MORSI_IGRADIENT},
-		{o_egrad, MORSI_EGRADIENT}, {o_lap, MORSI_LAPLACIAN}, {o_enh, MORSI_ENHANCE},
-		{o_str, MORSI_OSCILLATION}, {o_top, MORSI_TOPHAT}, {o_bot, MORSI_BOTHAT}
-	};
-	for (int i = 0; i < 12; i++)
-		if (t[i].out) run(t[i].op, t[i].out, x, w, h, e);
+	float *const out[12] = {o_ero, o_dil, o_ope, o_clo, o_grad, o_igrad, o_egrad, o_lap, o_enh, o_str, o_top, o_bot};
+	int rc = morsi_cuda_apply_all(e, x, out, w, h, 1);
+	if (rc != MORSI_OK) {
+		fprintf(stderr, "FAIL(\"morsi_all\"): libmorsi_cuda: %s: %s\n", morsi_cuda_strerror(rc), morsi_cuda_last_error());
+		exit(-1);
+	}
 }
 
 int *build_disk(float radius) { return morsi_build_disk(radius); }

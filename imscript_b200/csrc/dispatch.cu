@@ -236,7 +236,7 @@ int morsi_run_tiled(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int 
 {
 	*handled = 0;
 	const OpPlan plan = morsi_op_plan(job.op);
-	if (plan.special || de->n < 1 || de->n > 8192 || !de->d_tile_offs) return MORSI_OK;
+	if (plan.special == 1 || de->n < 1 || de->n > 8192 || !de->d_tile_offs) return MORSI_OK;
 	static const bool off = getenv("MORSI_TILED") && !strcmp(getenv("MORSI_TILED"), "0");
 	if (off) return MORSI_OK;
 	TiledLaunch t;
@@ -250,6 +250,27 @@ int morsi_run_tiled(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int 
 	// oscillation's last pass needs two tiles
 	const size_t worst = t.smem + ((plan.t_min && plan.t_max) ? (size_t)t.g.pw * t.g.ph * sizeof(float) : 0);
 	if (worst > 200 * 1024) return MORSI_OK;
+	if (plan.special == 2) {
+		// rank: one pass, no temporaries, exact in any order (no gated re-run needed)
+		static bool attr_set = false;
+		if (!attr_set) { cudaFuncSetAttribute(k_tiled_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+		const int rows_y = (job.y_rows + TILED_TY - 1) / TILED_TY;
+		for (int r0 = 0; r0 < rows_y; r0 += 65535) {
+			const int nb = rows_y - r0 < 65535 ? rows_y - r0 : 65535;
+			MedianArgs m;
+			m.x_src = Band{job.x, job.x_row0, job.x_pstride};
+			m.y = job.y + (long long)r0 * TILED_TY * job.w; m.y_pstride = job.y_pstride;
+			m.y_row0 = job.y_row0 + r0 * TILED_TY;
+			m.y_rows = job.y_rows - r0 * TILED_TY < nb * TILED_TY ? job.y_rows - r0 * TILED_TY : nb * TILED_TY;
+			m.w = job.w; m.h = job.h; m.offs = de->d_offs; m.n = de->n; m.gate = nullptr;
+			dim3 grid((job.w + TILED_TX - 1) / TILED_TX, nb, job.planes);
+			k_tiled_rank<<<grid, dim3(32, 8), t.smem, job.stream>>>(m, t.g);
+			morsi_count_launch(1);
+		}
+		MORSI_CU(cudaGetLastError());
+		*handled = 6;                                  // complete: the caller skips the gated re-run
+		return MORSI_OK;
+	}
 	int rc = run_exact_chunked(c, de, job, nullptr, &t);
 	if (rc) return rc;
 	*handled = 1;
@@ -275,11 +296,12 @@ int morsi_dispatch(MorsiCtx *c, const int *e, const MorsiJob &job)
 		if (!handled && !old_march) { rc = morsi_run_disk(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 2; }
 		if (!handled) { rc = morsi_run_march(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 3; }
 		if (!handled) { rc = morsi_run_median(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 4; }
-		if (!handled) { rc = morsi_run_tiled(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 5; }
+		if (!handled) { rc = morsi_run_tiled(c, de, job, flag, &handled); if (rc) return rc; if (handled == 1) handled = 5; }
 		if (getenv("MORSI_CUDA_TRACE"))
 			fprintf(stderr, "morsi_cuda: op %d n=%d %dx%dx%d rows [%d,+%d): %s\n", job.op, de->n, job.w, job.h, job.planes,
 				job.y_row0, job.y_rows, handled == 1 ? "small" : handled == 2 ? "disk" : handled == 3 ? "march (old)" :
-				handled == 4 ? "median" : handled == 5 ? "tiled" : "exact only");
+				handled == 4 ? "median" : handled == 5 ? "tiled" : handled == 6 ? "tiled rank" : "exact only");
+		if (handled == 6) return MORSI_OK;             // rank from tiles is exact as it stands
 		if (handled)
 			return path == 2 ? MORSI_OK : run_exact_chunked(c, de, job, flag);
 	}

@@ -310,9 +310,13 @@ __global__ void __launch_bounds__(256) k_small_1(SmallArgs p)
 }
 
 // ---- two stages fused ---------------------------------------------------------
-template <int MASK, bool VEC, bool OSC>
+// S1: the first stage is a minimum (0: opening, tophat), a maximum (1: closing,
+// bothat), or taken from p.stage1_max at run time (-1); EPI as in k_small_1.
+template <int MASK, bool VEC, bool OSC, int S1, int EPI>
 __global__ void __launch_bounds__(256) k_small_2(SmallArgs p)
 {
+	const bool s1max = S1 < 0 ? p.stage1_max != 0 : S1 == 1;
+	constexpr bool CT = EPI >= 0;
 	const int lane = threadIdx.x;
 	const int x0 = (blockIdx.x * 32 + lane) * 4;
 	const int plane = blockIdx.z;
@@ -366,8 +370,8 @@ __global__ void __launch_bounds__(256) k_small_2(SmallArgs p)
 						v1 = red3x3<MASK, false>(iu, im, id, c, p.mask);
 						v2 = red3x3<MASK, true>(iu, im, id, c, p.mask);
 					} else {
-						v1 = p.stage1_max ? red3x3<MASK, true>(iu, im, id, c, p.mask)
-						                  : red3x3<MASK, false>(iu, im, id, c, p.mask);
+						v1 = s1max ? red3x3<MASK, true>(iu, im, id, c, p.mask)
+						           : red3x3<MASK, false>(iu, im, id, c, p.mask);
 					}
 					const bool ok = trow && cok[c];
 					t1[u][c] = ok ? v1 : nan;
@@ -386,13 +390,13 @@ __global__ void __launch_bounds__(256) k_small_2(SmallArgs p)
 							// closing - opening: A = min over dilation, B = max over erosion
 							a = red3x3<MASK, false>(t2[(u + 1) % 3], t2[(u + 2) % 3], t2[u % 3], c, p.mask);
 							b = red3x3<MASK, true>(tu, tm, td, c, p.mask);
-						} else if (p.stage1_max) {
+						} else if (s1max) {
 							a = red3x3<MASK, false>(tu, tm, td, c, p.mask);
 						} else {
 							b = red3x3<MASK, true>(tu, tm, td, c, p.mask);
 						}
 						// x at row j-2: input slot of row j-2 is u % 3, columns offset by 2
-						o[c] = apply_epi(p.epi, a, b, iu[c + 2]);
+						o[c] = CT ? epilogue<CT ? EPI : 0>(a, b, iu[c + 2]) : apply_epi(p.epi, a, b, iu[c + 2]);
 					}
 					store_row<VEC>(yp + (long long)(j - 2 - p.y_row0) * p.w, x0, p.w, o);
 				}
@@ -424,8 +428,19 @@ static void launch_small_t(const SmallArgs &a, int stages, bool osc, dim3 grid, 
 		}
 		k_small_1<MASK, VEC, -1, 3><<<grid, block, 0, s>>>(a);
 	}
-	else if (osc) k_small_2<MASK, VEC, true><<<grid, block, 0, s>>>(a);
-	else k_small_2<MASK, VEC, false><<<grid, block, 0, s>>>(a);
+	else if (osc) {
+		if (VEC && MASK >= 0) k_small_2<MASK, VEC, true, -1, EPI_A_SUB_B><<<grid, block, 0, s>>>(a);
+		else k_small_2<MASK, VEC, true, -1, -1><<<grid, block, 0, s>>>(a);
+	} else {
+		if (VEC && MASK >= 0) {
+			// opening, closing, tophat, bothat with everything known at compile time
+			if (!a.stage1_max && a.epi == EPI_B) { k_small_2<MASK, VEC, false, 0, EPI_B><<<grid, block, 0, s>>>(a); return; }
+			if (a.stage1_max && a.epi == EPI_A) { k_small_2<MASK, VEC, false, 1, EPI_A><<<grid, block, 0, s>>>(a); return; }
+			if (!a.stage1_max && a.epi == EPI_X_SUB_B) { k_small_2<MASK, VEC, false, 0, EPI_X_SUB_B><<<grid, block, 0, s>>>(a); return; }
+			if (a.stage1_max && a.epi == EPI_A_SUB_X) { k_small_2<MASK, VEC, false, 1, EPI_A_SUB_X><<<grid, block, 0, s>>>(a); return; }
+		}
+		k_small_2<MASK, VEC, false, -1, -1><<<grid, block, 0, s>>>(a);
+	}
 }
 
 // returns MORSI_OK and *handled = 1 when it launched the job
@@ -457,10 +472,10 @@ int morsi_run_small(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int 
 	// 76 % of the HBM copy rate, 64 rows 72 %, 270 rows 60 %): the CTAs in flight
 	// then sweep the image like a copy does and the re-read halo rows hit in L2;
 	// small images get even shorter marches so that every SM has warps to run.
-	// Two stages: longer marches, the warm-up is 4 rows of two reductions.
+	// Two stages: longer marches, the warm-up is 4 rows of two reductions (32 rows measured best).
 	const int gx = (job.w + (128 << wxl) - 1) / (128 << wxl);
 	static const int forced_rpw = getenv("MORSI_SMALL_RPW") ? atoi(getenv("MORSI_SMALL_RPW")) : 0;
-	int rpw = plan.stages == 1 ? 8 : 64;
+	int rpw = plan.stages == 1 ? 8 : 32;
 	const int min_rpw = plan.stages == 1 ? 2 : 8;
 	while (rpw > min_rpw && (long long)gx * ((job.y_rows + rpw * segs - 1) / (rpw * segs)) * job.planes < 4LL * c->sm_count)
 		rpw /= 2;

@@ -99,3 +99,54 @@ __global__ void __launch_bounds__(256) k_tiled_minmax(ExactArgs p, TiledGeom g, 
 		}
 	}
 }
+
+// ---- rank (src/morsi.c:122-139) from the same tiles ------------------------------------
+// u = the pixel itself; the count of finite neighbours below u does not depend
+// on the element order and treats +0/-0 like the reference's `<`: exact as is.
+__global__ void __launch_bounds__(256) k_tiled_rank(MedianArgs p, TiledGeom g)
+{
+	extern __shared__ float tiled_smem[];
+	const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
+	const int plane = blockIdx.z;
+	const int bx = blockIdx.x * TILED_TX, by = blockIdx.y * TILED_TY;
+	const int pw = g.pw, ph = g.ph;
+	float *tile = tiled_smem;
+	int *offs = reinterpret_cast<int *>(tiled_smem + pw * ph);
+	bool unused = false;
+	tiled_load(tile, p.x_src, plane, p.w, p.h, bx + g.xmin, p.y_row0 + by + g.ymin, pw, ph, tid, unused);
+	for (int k = tid; k < p.n; k += 256) offs[k] = g.tile_offs[k];
+	__syncthreads();
+
+	float u[2][4];
+	int cnt[2][4];
+#pragma unroll
+	for (int r = 0; r < 2; r++)
+#pragma unroll
+		for (int c = 0; c < 4; c++) {
+			// outside the image u is NaN and every comparison fails; those outputs are not stored anyway
+			u[r][c] = band_pixel(p.x_src, plane, p.w, p.h, bx + tx + 32 * c, p.y_row0 + by + ty + 8 * r);
+			cnt[r][c] = 0;
+		}
+	const float *q = tile + ty * pw + tx;
+	const int row8 = 8 * pw;
+	for (int k = 0; k < p.n; k++) {
+		const int o = offs[k];
+#pragma unroll
+		for (int r = 0; r < 2; r++)
+#pragma unroll
+			for (int c = 0; c < 4; c++) {
+				const float v = q[o + r * row8 + 32 * c];
+				cnt[r][c] += (isfinite(v) && v < u[r][c]) ? 1 : 0;
+			}
+	}
+#pragma unroll
+	for (int r = 0; r < 2; r++) {
+		const int jj = by + ty + 8 * r;
+		if (jj >= p.y_rows) continue;
+#pragma unroll
+		for (int c = 0; c < 4; c++) {
+			const int i = bx + tx + 32 * c;
+			if (i < p.w) p.y[plane * p.y_pstride + (long long)jj * p.w + i] = (float)cnt[r][c];
+		}
+	}
+}

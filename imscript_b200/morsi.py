@@ -38,10 +38,14 @@ def build_disk(radius):
 def morsi_all(o_ero, o_dil, o_ope, o_clo, o_grad, o_igrad, o_egrad, o_lap, o_enh, o_str,
               o_top, o_bot, x, w, h, e):
     """src/morsi.c:278-310: None outputs are skipped."""
-    table = [(o_ero, "erosion"), (o_dil, "dilation"), (o_ope, "opening"), (o_clo, "closing"),
-             (o_grad, "gradient"), (o_igrad, "igradient"), (o_egrad, "egradient"),
-             (o_lap, "laplacian"), (o_enh, "enhance"), (o_str, "oscillation"),
-             (o_top, "tophat"), (o_bot, "bothat")]
-    for out, op in table:
+    import ctypes
+    import numpy as np
+    outs = [o_ero, o_dil, o_ope, o_clo, o_grad, o_igrad, o_egrad, o_lap, o_enh, o_str, o_top, o_bot]
+    xs = np.ascontiguousarray(x, dtype=np.float32)
+    ptrs = (ctypes.c_void_p * 12)()
+    for k, out in enumerate(outs):
         if out is not None:
-            _run(op, out, x, w, h, e)
+            assert out.dtype == np.float32 and out.flags["C_CONTIGUOUS"] and out.size >= w * h
+            ptrs[k] = out.ctypes.data
+    ee = np.ascontiguousarray(e, dtype=np.int32)
+    _b.check(_b.lib().morsi_cuda_apply_all(ee.ctypes.data_as(_b._i32p), xs.ctypes.data, ptrs, w, h, 1))

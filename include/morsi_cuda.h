@@ -106,6 +106,13 @@ void morsi_cuda_shutdown(void);
 int morsi_cuda_apply(int op, const int *e, const float *x, float *y,
 		int w, int h, int planes);
 
+/* morsi_all (src/morsi.c:278-310) for host pointers: out[] = {erosion, dilation,
+ * opening, closing, gradient, igradient, egradient, laplacian, enhance,
+ * oscillation ("o_str"), tophat, bothat}; NULL entries are skipped.  The input
+ * is copied to the device once; every result equals the single operation's. */
+int morsi_cuda_apply_all(const int *e, const float *x, float *const out[12],
+		int w, int h, int planes);
+
 /* Same computation on DEVICE-resident planar data (row pitch = w), enqueued on
  * `stream` (a cudaStream_t; NULL = the context's stream) of the current
  * device, asynchronous. d_x and d_y must not overlap. */

@@ -204,6 +204,28 @@ def test_reference_signature_mirror():
             assert_same(out.reshape(h, w), o.apply(op, e, x), "morsi_all " + op)
 
 
+def test_apply_all_outputs():
+    """morsi_cuda_apply_all (src/morsi.c:278-310): 12 outputs of one upload, several planes, some skipped"""
+    import ctypes
+    o = oracle()
+    names = ["erosion", "dilation", "opening", "closing", "gradient", "igradient",
+             "egradient", "laplacian", "enhance", "oscillation", "tophat", "bothat"]
+    h, w = 150, 203
+    x = np.stack([M.synth_host(w, h, plane=p, seed=61, dist=2 if p == 1 else 0) for p in range(2)])
+    for ename, skip in [("disk7", ()), ("cross", (1, 6)), ("dysk4", (0, 2, 4, 8, 10))]:
+        e = o.element(ename)
+        outs = [None if k in skip else np.empty_like(x) for k in range(12)]
+        ptrs = (ctypes.c_void_p * 12)()
+        for k, out in enumerate(outs):
+            if out is not None:
+                ptrs[k] = out.ctypes.data
+        ee = np.ascontiguousarray(e, dtype=np.int32)
+        M.binding.check(M.lib().morsi_cuda_apply_all(ee.ctypes.data_as(M.binding._i32p), x.ctypes.data, ptrs, w, h, 2))
+        for k, out in enumerate(outs):
+            if out is not None:
+                assert_same(out, o.apply(names[k], e, x), f"apply_all {ename} {names[k]}")
+
+
 def test_full_size_properties():
     """BASELINE config sizes through size-independent properties (the oracle
     would need hours): duality, extensivity, idempotence, linearity under
