@@ -494,7 +494,11 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 					if (e0) load_cols<C>(xq, xv0);
 					if (e1) load_cols<C>(xq + pitch, xv1);
 				}
+				#ifdef DISK_NO_ZCHECK   /* experiment: how much does the -0.0 scan cost the first stage? (results unsafe) */
+				D::step(acc, hs, s % (R + 1), rowA, rowA + RP, zmin, false,
+#else
 				D::step(acc, hs, s % (R + 1), rowA, rowA + RP, zmin, reads_input,
+#endif
 					// the group has been read (its loads were issued before this
 					// arrive and complete long before a refill can land)
 					[&]() { if (pos == GP - 1 && lane0) mbar_arrive(grp_empty); },

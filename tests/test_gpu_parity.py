@@ -130,7 +130,10 @@ def test_median_fast_kernels(quad, monkeypatch):
     for (h, w) in [(151, 203), (64, 130), (37, 66)]:
         x = np.stack([M.synth_host(w, h, plane=p, seed=51, dist=p) for p in range(3)])
         x[x == 0] = 0.0
-        for name in ["disk2.5", "disk3", "disk3.5", "disk4", "disk4.2", "disk5", "cross", "square"]:
+        for name in ["disk2.5", "disk3", "disk3.5", "disk4", "disk4.2", "disk5", "disk5.1", "disk6", "disk7",
+                     "cross", "square"]:
+            if quad == "0" and name in ("disk5.1", "disk6", "disk7") and h > 64:
+                continue                     # without the quad kernel these take the (slow) exact path
             e = o.element(name)
             assert_same(M.apply("median", e, x), o.apply("median", e, x), f"{name} median {w}x{h} quad={quad}")
 

@@ -30,6 +30,9 @@ SHAPES = {  # id: (reach, half-widths per row) -- must match shapes.cuh
     3: (3, [2, 3, 3, 3, 3, 3, 2]),
     4: (4, [1, 2, 3, 4, 4, 4, 3, 2, 1]),
     5: (4, [2, 3, 4, 4, 4, 4, 4, 3, 2]),
+    6: (5, [1, 3, 4, 4, 5, 5, 5, 4, 4, 3, 1]),
+    7: (5, [3, 4, 5, 5, 5, 5, 5, 5, 5, 4, 3]),
+    8: (6, [3, 4, 5, 6, 6, 6, 6, 6, 6, 6, 5, 4, 3]),
 }
 
 
