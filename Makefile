@@ -12,7 +12,7 @@ OUT    := imscript_b200/lib
 OBJ    := build/obj
 
 CU_SRCS := $(wildcard $(SRC)/*.cu)
-CU_OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(CU_SRCS))
+CU_OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(CU_SRCS)) $(OBJ)/k_disk_p1.o $(OBJ)/k_disk_p2.o $(OBJ)/k_disk_p3.o
 HDRS    := $(wildcard $(SRC)/*.cuh) $(wildcard $(SRC)/*.h) include/morsi_cuda.h
 
 all: $(OUT)/libmorsi_cuda.so $(OUT)/libmorsi_compat.so cli
@@ -20,6 +20,11 @@ all: $(OUT)/libmorsi_cuda.so $(OUT)/libmorsi_compat.so cli
 $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJ)/$*.ptxas.log || (cat $(OBJ)/$*.ptxas.log; false)
+
+# k_disk.cu holds 17 shapes x 12 kernels: compiled as four units so that -j parallelises
+$(OBJ)/k_disk_p%.o: $(SRC)/k_disk.cu $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -DMORSI_DISK_PART=$* -c $< -o $@ 2> $(OBJ)/k_disk_p$*.ptxas.log || (cat $(OBJ)/k_disk_p$*.ptxas.log; false)
 
 $(OBJ)/element.o: $(SRC)/element.c $(HDRS)
 	@mkdir -p $(OBJ)

@@ -203,7 +203,9 @@ static int run_minmax_passes(MorsiCtx *c, const DevElement *de, const MorsiJob &
 static int run_exact_chunked(MorsiCtx *c, const DevElement *de, const MorsiJob &job, const int *gate, const TiledLaunch *tl = nullptr)
 {
 	const OpPlan plan = morsi_op_plan(job.op);
-	const long long budget = 256LL << 20;
+	// the gated re-run is a no-op nearly always: fewer, larger chunks keep its launch count down
+	// (C4: 6 launches per step instead of 50)
+	const long long budget = (gate ? 2048LL : 256LL) << 20;
 	const int halo = plan.stages == 2 ? (de->info.ymax - de->info.ymin + 1) : 0;
 	long long row_bytes = (long long)job.w * 4;
 	long long rows_fit = budget / row_bytes - halo;

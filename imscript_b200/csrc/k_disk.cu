@@ -133,26 +133,25 @@ __device__ __forceinline__ float disk_epi(int epi, float a, float b, float x)
 }
 
 // Epilogue with extra operands (single-stage kernel), kept out of line: the
-// unrolled march calls it from 2(R+1) places.
+// unrolled march calls it from 2(R+1) places.  Arithmetic only: the operands
+// are loaded by the caller BEFORE the step's reductions, so that their latency
+// hides behind them (a load inside this call would stall every step).
 template <bool ISMAX>
-__device__ __noinline__ void disk_emit_general(float *q, const float *qx, const float *qo, int epi, int ncol,
-		float m0, float m1, float m2, float m3)
+__device__ __noinline__ float4 disk_epi4(int epi, float m0, float m1, float m2, float m3,
+		float o0, float o1, float o2, float o3, float x0, float x1, float x2, float x3)
 {
-	float m[4] = {m0, m1, m2, m3};
-	float xv[4] = {0.f, 0.f, 0.f, 0.f}, ov[4] = {0.f, 0.f, 0.f, 0.f}, out[4];
-	if (qx) {
-		if (ncol == 4) { float4 t = __ldg((const float4 *)qx); xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w; }
-		else { float2 t = __ldg((const float2 *)qx); xv[0] = t.x; xv[1] = t.y; }
+	const float m[4] = {m0, m1, m2, m3}, ov[4] = {o0, o1, o2, o3}, xv[4] = {x0, x1, x2, x3};
+	float out[4] = {m0, m1, m2, m3};
+	// one dispatch per call, the four columns inside each case
+#define CASE(E) case E: _Pragma("unroll") for (int c = 0; c < 4; c++) \
+		out[c] = ISMAX ? epilogue<E>(ov[c], m[c], xv[c]) : epilogue<E>(m[c], ov[c], xv[c]); break;
+	switch (epi) {
+	CASE(EPI_B_SUB_A) CASE(EPI_X_SUB_A) CASE(EPI_B_SUB_X) CASE(EPI_LAP) CASE(EPI_ENH) CASE(EPI_BLUR)
+	CASE(EPI_A_SUB_B) CASE(EPI_X_SUB_B) CASE(EPI_A_SUB_X) CASE(EPI_IBLUR) CASE(EPI_EBLUR) CASE(EPI_CBLUR)
+	default: break;                                  // EPI_A / EPI_B: the reduction itself
 	}
-	if (qo) {
-		if (ncol == 4) { float4 t = __ldg((const float4 *)qo); ov[0] = t.x; ov[1] = t.y; ov[2] = t.z; ov[3] = t.w; }
-		else { float2 t = __ldg((const float2 *)qo); ov[0] = t.x; ov[1] = t.y; }
-	}
-#pragma unroll
-	for (int c = 0; c < 4; c++)
-		out[c] = ISMAX ? disk_epi(epi, ov[c], m[c], xv[c]) : disk_epi(epi, m[c], ov[c], xv[c]);
-	if (ncol == 4) *(float4 *)q = make_float4(out[0], out[1], out[2], out[3]);
-	else *(float2 *)q = make_float2(out[0], out[1]);
+#undef CASE
+	return make_float4(out[0], out[1], out[2], out[3]);
 }
 
 // ---- compile-time geometry ---------------------------------------------------------
@@ -349,7 +348,7 @@ __device__ __forceinline__ void load_cols(const float *q, float (&m)[C])
 // first stage, rare path: a temporary row pair that touches the image border
 // (scalars by value: arrays by reference would force the caller's rows into
 // local memory on the common path too)
-__device__ __noinline__ void disk_store_tmp_masked(float *q0, float *q1, int ncol, unsigned colmask, bool row0_ok, bool row1_ok,
+static __device__ __noinline__ void disk_store_tmp_masked(float *q0, float *q1, int ncol, unsigned colmask, bool row0_ok, bool row1_ok,
 		float a0, float a1, float a2, float a3, float b0, float b1, float b2, float b3)
 {
 	const float nan = CUDART_NAN_F;
@@ -489,10 +488,19 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 				const int o0 = 2 * g - 2 * R;
 				const bool e0 = col_ok && o0 >= 0 && o0 < nout;
 				const bool e1 = col_ok && o0 + 1 >= 0 && o0 + 1 < nout;
-				float xv0[C], xv1[C];
+				float xv0[C], xv1[C], ov0[C], ov1[C];
 				if (TWO && HASX) {
 					if (e0) load_cols<C>(xq, xv0);
 					if (e1) load_cols<C>(xq + pitch, xv1);
+				}
+				if (!TWO && !plain) {
+					// operands of the epilogue, in flight during the reductions below
+#pragma unroll
+					for (int c = 0; c < C; c++) { xv0[c] = 0.f; xv1[c] = 0.f; ov0[c] = 0.f; ov1[c] = 0.f; }
+					if (e0 && xq) load_cols<C>(xq, xv0);
+					if (e1 && xq) load_cols<C>(xq + pitch, xv1);
+					if (e0 && oq) load_cols<C>(oq, ov0);
+					if (e1 && oq) load_cols<C>(oq + pitch, ov1);
 				}
 				#ifdef DISK_NO_ZCHECK   /* experiment: how much does the -0.0 scan cost the first stage? (results unsafe) */
 				D::step(acc, hs, s % (R + 1), rowA, rowA + RP, zmin, false,
@@ -551,12 +559,21 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 					} else {
 						if (e0) {
 							if (plain) store_cols<C>(yq, m0);
-							else disk_emit_general<ISMAX>(yq, xq, oq, epi, C, m0[0], m0[1], C == 4 ? m0[2] : 0.f, C == 4 ? m0[3] : 0.f);
+							else {
+								const float4 r = disk_epi4<ISMAX>(epi, m0[0], m0[1], C == 4 ? m0[2] : 0.f, C == 4 ? m0[3] : 0.f,
+										ov0[0], ov0[1], C == 4 ? ov0[2] : 0.f, C == 4 ? ov0[3] : 0.f,
+										xv0[0], xv0[1], C == 4 ? xv0[2] : 0.f, C == 4 ? xv0[3] : 0.f);
+								if (C == 4) *(float4 *)yq = r; else *(float2 *)yq = make_float2(r.x, r.y);
+							}
 						}
 						if (e1) {
 							if (plain) store_cols<C>(yq + pitch, m1);
-							else disk_emit_general<ISMAX>(yq + pitch, xq ? xq + pitch : nullptr, oq ? oq + pitch : nullptr,
-									epi, C, m1[0], m1[1], C == 4 ? m1[2] : 0.f, C == 4 ? m1[3] : 0.f);
+							else {
+								const float4 r = disk_epi4<ISMAX>(epi, m1[0], m1[1], C == 4 ? m1[2] : 0.f, C == 4 ? m1[3] : 0.f,
+										ov1[0], ov1[1], C == 4 ? ov1[2] : 0.f, C == 4 ? ov1[3] : 0.f,
+										xv1[0], xv1[1], C == 4 ? xv1[2] : 0.f, C == 4 ? xv1[3] : 0.f);
+								if (C == 4) *(float4 *)(yq + pitch) = r; else *(float2 *)(yq + pitch) = make_float2(r.x, r.y);
+							}
 						}
 						// pitched copies (w % 4 != 0): the pad columns of a row stay NaN, the
 						// result may be the source of a later pass (oscillation)
@@ -742,11 +759,58 @@ static int disk_shape(MorsiCtx *c, const DiskArgs &a, int planes, bool ismax, bo
 	return disk_shape_c<ID, 4>(c, a, planes, ismax, two, st);
 }
 
-// development aid: -DMORSI_DISK_IDS="T(8) T(13)" compiles a subset of the shapes
+// The shapes are compiled in four translation units -- this source with
+// -DMORSI_DISK_PART=0..3 (Makefile) -- so that the build parallelises; part 0
+// also holds the host logic.  Development aid: -DMORSI_DISK_IDS="T(8) T(13)"
+// compiles a subset of the shapes, all in part 0.
+#ifndef MORSI_DISK_PART
+#define MORSI_DISK_PART 0
+#endif
 #ifdef MORSI_DISK_IDS
-#define DISK_IDS MORSI_DISK_IDS
+#define DISK_IDS_P0 MORSI_DISK_IDS
+#define DISK_IDS_P1
+#define DISK_IDS_P2
+#define DISK_IDS_P3
 #else
-#define DISK_IDS T(0) T(1) T(2) T(3) T(4) T(5) T(6) T(7) T(8) T(9) T(10) T(11) T(12) T(13) T(16) T(17) T(18)
+#define DISK_IDS_P0 T(0) T(1) T(2) T(3) T(4) T(5) T(6) T(7)
+#define DISK_IDS_P1 T(8) T(9) T(10) T(11)
+#define DISK_IDS_P2 T(12) T(16) T(17)
+#define DISK_IDS_P3 T(13) T(18)
+#endif
+#define DISK_IDS DISK_IDS_P0 DISK_IDS_P1 DISK_IDS_P2 DISK_IDS_P3
+#if MORSI_DISK_PART == 0
+#define DISK_IDS_MINE DISK_IDS_P0
+#elif MORSI_DISK_PART == 1
+#define DISK_IDS_MINE DISK_IDS_P1
+#elif MORSI_DISK_PART == 2
+#define DISK_IDS_MINE DISK_IDS_P2
+#else
+#define DISK_IDS_MINE DISK_IDS_P3
+#endif
+
+// launch shape `id` if this part compiled it; -2: not mine
+#define DISK_PART_FN2(N) morsi_disk_launch_part##N
+#define DISK_PART_FN(N) DISK_PART_FN2(N)
+int morsi_disk_launch_part0(int id, MorsiCtx *c, const DiskArgs &a, int planes, bool ismax, bool two, cudaStream_t st);
+int morsi_disk_launch_part1(int id, MorsiCtx *c, const DiskArgs &a, int planes, bool ismax, bool two, cudaStream_t st);
+int morsi_disk_launch_part2(int id, MorsiCtx *c, const DiskArgs &a, int planes, bool ismax, bool two, cudaStream_t st);
+int morsi_disk_launch_part3(int id, MorsiCtx *c, const DiskArgs &a, int planes, bool ismax, bool two, cudaStream_t st);
+
+int DISK_PART_FN(MORSI_DISK_PART)(int id, MorsiCtx *c, const DiskArgs &a, int planes, bool ismax, bool two, cudaStream_t st)
+{
+	switch (id) {
+#define T(ID) case ID: return disk_shape<ID>(c, a, planes, ismax, two, st);
+	DISK_IDS_MINE
+#undef T
+	}
+	return -2;
+}
+
+#if MORSI_DISK_PART == 0
+#ifdef MORSI_DISK_IDS   // single-unit development build: the other parts are empty
+int morsi_disk_launch_part1(int, MorsiCtx *, const DiskArgs &, int, bool, bool, cudaStream_t) { return -2; }
+int morsi_disk_launch_part2(int, MorsiCtx *, const DiskArgs &, int, bool, bool, cudaStream_t) { return -2; }
+int morsi_disk_launch_part3(int, MorsiCtx *, const DiskArgs &, int, bool, bool, cudaStream_t) { return -2; }
 #endif
 
 template <int ID>
@@ -769,12 +833,12 @@ static int find_shape(const RowRunPlan &rr)
 
 static int launch_by_id(int id, MorsiCtx *c, const DiskArgs &a, int planes, bool ismax, bool two, cudaStream_t st)
 {
-	switch (id) {
-#define T(ID) case ID: return disk_shape<ID>(c, a, planes, ismax, two, st);
-	DISK_IDS
-#undef T
-	}
-	return morsi_set_error(MORSI_ERR_INVALID, "no such shape %d", id);
+	int rc = morsi_disk_launch_part0(id, c, a, planes, ismax, two, st);
+	if (rc == -2) rc = morsi_disk_launch_part1(id, c, a, planes, ismax, two, st);
+	if (rc == -2) rc = morsi_disk_launch_part2(id, c, a, planes, ismax, two, st);
+	if (rc == -2) rc = morsi_disk_launch_part3(id, c, a, planes, ismax, two, st);
+	if (rc == -2) return morsi_set_error(MORSI_ERR_INVALID, "no such shape %d", id);
+	return rc;
 }
 
 // One reduction pass over `src` for output rows [row0,row0+rows) into `dst`.
@@ -949,3 +1013,4 @@ int morsi_run_disk(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *
 	*handled = 1;
 	return MORSI_OK;
 }
+#endif   // MORSI_DISK_PART == 0

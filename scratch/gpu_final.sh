@@ -22,3 +22,8 @@ done
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>&1; cat gpurun_out/bench_ref.json | cut -c1-300
 python -c "import __graft_entry__ as g; g.smoke()"
 rm -f gpurun_out/*_source.csv.bak; du -sh gpurun_out
+# extra: the fused 3x3 two-stage kernel (cross opening of the C5 batch)
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_small_2 -s 3 -c 1 -o /tmp/ksmall2 -f python scratch/time_op.py cross opening 1920 1080 192 0 3 > gpurun_out/ncu_ksmall2.log 2>&1
+ncu -i /tmp/ksmall2.ncu-rep --page source --csv > gpurun_out/ksmall2_source.csv 2>/dev/null
+python scratch/ncu_summary.py /tmp/ksmall2.ncu-rep > gpurun_out/ksmall2_summary.txt 2>&1
+for op in erosion opening gradient; do MORSI_CUDA_PATH=fast python scratch/time_op.py disk7 $op 4096 4096 3 0 20; done
