@@ -84,7 +84,7 @@ template <int HALO>
 struct RawRow {
 	float c[4];
 	float e[HALO];      // lane 0: columns x0-1 (, x0-2); lane 31: columns x0+4 (, x0+5)
-	unsigned ok;        // VEC: bit 0: c[] exist, bit 1+k: e[k] exists (absent samples are NaN on use)
+	unsigned ok;        // VEC: bit 0: c[] exist, bit 1+k: e[k] exists or is unused (absent samples are NaN on use)
 };
 
 // VEC: unconditional loads (absent samples read the plane's first floats
@@ -106,7 +106,7 @@ __device__ __forceinline__ void fetch_row(const float *plane, int row0, int w, i
 			const int off = lane == 0 ? -1 - k : 4 + k;
 			const bool eok = rowok && ((lane == 0 && x0 - 1 - k >= 0 && x0 - 1 - k < w) || (lane == 31 && x0 + 4 + k < w));
 			r.e[k] = __ldg(eok ? row + x0 + off : plane);
-			ok |= eok ? (2u << k) : 0u;
+			ok |= (eok || (lane != 0 && lane != 31)) ? (2u << k) : 0u;   // inner lanes never use e[]
 		}
 		r.ok = ok;
 		return;
@@ -140,13 +140,20 @@ __device__ __forceinline__ void assemble_row(const RawRow<HALO> &r0, int lane,
 {
 	RawRow<HALO> r = r0;
 	const float nan = CUDART_NAN_F;
-	if (!(r.ok & 1u)) { r.c[0] = nan; r.c[1] = nan; r.c[2] = nan; r.c[3] = nan; }
+	// absent samples (rows outside the image, columns beyond it): rare, so a branch, not selects
+	constexpr unsigned full = (2u << HALO) - 1u;
+	if (r.ok != full && r.ok != ~0u) {
+		if (!(r.ok & 1u)) { r.c[0] = nan; r.c[1] = nan; r.c[2] = nan; r.c[3] = nan; }
 #pragma unroll
-	for (int k = 0; k < HALO; k++) if (!(r.ok & (2u << k))) r.e[k] = nan;
-	negzero |= (__float_as_uint(r.c[0]) == 0x80000000u) | (__float_as_uint(r.c[1]) == 0x80000000u) |
-	           (__float_as_uint(r.c[2]) == 0x80000000u) | (__float_as_uint(r.c[3]) == 0x80000000u);
-#pragma unroll
-	for (int k = 0; k < HALO; k++) negzero |= (__float_as_uint(r.e[k]) == 0x80000000u);
+		for (int k = 0; k < HALO; k++) if (!(r.ok & (2u << k))) r.e[k] = nan;
+	}
+	// -0.0 is INT_MIN as a signed word: a running 3-input integer minimum sees it
+	int z = (int)negzero;
+	z = min(min(z, __float_as_int(r.c[0])), __float_as_int(r.c[1]));
+	z = min(min(z, __float_as_int(r.c[2])), __float_as_int(r.c[3]));
+	if (HALO == 2) z = min(min(z, __float_as_int(r.e[0])), __float_as_int(r.e[HALO - 1]));
+	else z = min(z, __float_as_int(r.e[0]));
+	negzero = (unsigned)z;
 #pragma unroll
 	for (int k = 0; k < 4; k++) v[HALO + k] = r.c[k];
 	float l1 = __shfl_up_sync(0xffffffffu, r.c[3], 1);
@@ -160,6 +167,48 @@ __device__ __forceinline__ void assemble_row(const RawRow<HALO> &r0, int lane,
 	if (lane == 31) { r1 = r.e[0]; if (HALO == 2) r2 = r.e[HALO - 1]; }
 	if (HALO == 1) { v[0] = l1; v[5] = r1; }
 	else { v[0] = l2; v[1] = l1; v[6] = r1; v[7] = r2; }
+}
+
+// Loop-invariant part of fetch_row's VEC path (k_small_2): column pointers with
+// absent columns redirected to the plane's first floats, which samples exist
+// column-wise, and the row clamp that keeps every load inside the band.
+template <int HALO>
+struct FetchCtx {
+	const float *pc;          // this thread's 4 columns of row `row0`
+	const float *pe[HALO];    // its edge columns (lanes 0 / 31), or a dummy
+	unsigned colbits;         // RawRow::ok of a row that exists
+	int row0, h, w;
+};
+
+template <int HALO>
+__device__ __forceinline__ FetchCtx<HALO> fetch_ctx(const float *plane, int row0, int w, int h, int x0, int lane)
+{
+	FetchCtx<HALO> f;
+	f.row0 = row0; f.h = h; f.w = w;
+	const bool cok = x0 < w;
+	f.pc = plane + (cok ? x0 : 0);
+	f.colbits = cok ? 1u : 0u;
+#pragma unroll
+	for (int k = 0; k < HALO; k++) {
+		const int off = lane == 0 ? -1 - k : 4 + k;
+		const bool eok = (lane == 0 && x0 - 1 - k >= 0 && x0 - 1 - k < w) || (lane == 31 && x0 + 4 + k < w);
+		f.pe[k] = plane + (eok ? x0 + off : 0);
+		f.colbits |= (eok || (lane != 0 && lane != 31)) ? (2u << k) : 0u;   // inner lanes never use e[]
+	}
+	return f;
+}
+
+// row j of the image; rows outside it load the nearest row (always inside the band) and are marked absent
+template <int HALO>
+__device__ __forceinline__ void fetch_row_vec(const FetchCtx<HALO> &f, int j, RawRow<HALO> &r)
+{
+	const int jc = min(max(j, 0), f.h - 1);
+	const long long off = (long long)(jc - f.row0) * f.w;
+	const float4 q = __ldg(reinterpret_cast<const float4 *>(f.pc + off));
+	r.c[0] = q.x; r.c[1] = q.y; r.c[2] = q.z; r.c[3] = q.w;
+#pragma unroll
+	for (int k = 0; k < HALO; k++) r.e[k] = __ldg(f.pe[k] + off);
+	r.ok = jc == j ? f.colbits : 0u;
 }
 
 #define SMALL_PF 3     // rows fetched ahead of the row being reduced
@@ -218,9 +267,12 @@ __device__ __forceinline__ void assemble1(const Raw1 &r, bool ok, bool eok, int 
 		if (!ok) q = make_float4(nan, nan, nan, nan);
 		if (!eok) e = nan;
 	}
-	negzero |= (__float_as_uint(q.x) == 0x80000000u) | (__float_as_uint(q.y) == 0x80000000u) |
-	           (__float_as_uint(q.z) == 0x80000000u) | (__float_as_uint(q.w) == 0x80000000u) |
-	           (__float_as_uint(e) == 0x80000000u);
+	// -0.0 is INT_MIN as a signed word: a running 3-input integer minimum sees it
+	int z = (int)negzero;
+	z = min(min(z, __float_as_int(q.x)), __float_as_int(q.y));
+	z = min(min(z, __float_as_int(q.z)), __float_as_int(q.w));
+	z = min(z, __float_as_int(e));
+	negzero = (unsigned)z;
 	const float l1 = __shfl_up_sync(0xffffffffu, q.w, 1);
 	const float r1 = __shfl_down_sync(0xffffffffu, q.x, 1);
 	v[0] = lane == 0 ? e : l1;
@@ -306,14 +358,14 @@ __global__ void __launch_bounds__(256) k_small_1(SmallArgs p)
 		}
 	}
 #undef ROW_OK
-	if (__any_sync(0xffffffffu, negzero) && lane == 0) atomicOr(p.flag, 1);
+	if (__any_sync(0xffffffffu, negzero == 0x80000000u) && lane == 0) atomicOr(p.flag, 1);
 }
 
 // ---- two stages fused ---------------------------------------------------------
 // S1: the first stage is a minimum (0: opening, tophat), a maximum (1: closing,
 // bothat), or taken from p.stage1_max at run time (-1); EPI as in k_small_1.
 template <int MASK, bool VEC, bool OSC, int S1, int EPI>
-__global__ void __launch_bounds__(256) k_small_2(SmallArgs p)
+__global__ void __launch_bounds__(256, OSC ? 2 : 3) k_small_2(SmallArgs p)
 {
 	const bool s1max = S1 < 0 ? p.stage1_max != 0 : S1 == 1;
 	constexpr bool CT = EPI >= 0;
@@ -337,18 +389,22 @@ __global__ void __launch_bounds__(256) k_small_2(SmallArgs p)
 	bool cok[6];
 #pragma unroll
 	for (int c = 0; c < 6; c++) cok[c] = (x0 - 1 + c >= 0) && (x0 - 1 + c < p.w);
+	const bool edge_thread = !(cok[0] && cok[5]);
 
 	// input rows j = y0-2 .. y1+1, slot (j-(y0-2)) % 3
 	// temporary row t = j-1 becomes available after loading row j; slot (t-(y0-1)) % 3
 	// output row t-1 = j-2 after temporary rows j-3, j-2, j-1 exist
 	RawRow<2> raw[SMALL_PF];
+	const FetchCtx<2> fc = fetch_ctx<2>(xp, p.x.row0, p.w, p.h, x0, lane);
+#define FETCH2(j, slot) do { if (VEC) fetch_row_vec<2>(fc, (j), slot); \
+		else fetch_row<2, VEC>(xp, p.x.row0, p.w, p.h, (j), x0, lane, slot); } while (0)
 #pragma unroll
 	for (int k = 0; k < SMALL_PF; k++)
-		fetch_row<2, VEC>(xp, p.x.row0, p.w, p.h, y0 - 2 + k, x0, lane, raw[k]);
+		FETCH2(y0 - 2 + k, raw[k]);
 	assemble_row<2>(raw[0], lane, in[0], negzero);
-	fetch_row<2, VEC>(xp, p.x.row0, p.w, p.h, y0 - 2 + SMALL_PF, x0, lane, raw[0]);
+	FETCH2(y0 - 2 + SMALL_PF, raw[0]);
 	assemble_row<2>(raw[1], lane, in[1], negzero);
-	fetch_row<2, VEC>(xp, p.x.row0, p.w, p.h, y0 - 1 + SMALL_PF, x0, lane, raw[1]);
+	FETCH2(y0 - 1 + SMALL_PF, raw[1]);
 	for (int jb = y0; jb <= y1 + 1; jb += 3) {
 #pragma unroll
 		for (int u = 0; u < 3; u++) {
@@ -356,7 +412,7 @@ __global__ void __launch_bounds__(256) k_small_2(SmallArgs p)
 			if (j <= y1 + 1) {
 				assemble_row<2>(raw[(u + 2) % 3], lane, in[(u + 2) % 3], negzero);
 				if (j + SMALL_PF <= y1 + 1)
-					fetch_row<2, VEC>(xp, p.x.row0, p.w, p.h, j + SMALL_PF, x0, lane, raw[(u + 2) % 3]);
+					FETCH2(j + SMALL_PF, raw[(u + 2) % 3]);
 				const float (&iu)[8] = in[u % 3];
 				const float (&im)[8] = in[(u + 1) % 3];
 				const float (&id)[8] = in[(u + 2) % 3];
@@ -373,9 +429,15 @@ __global__ void __launch_bounds__(256) k_small_2(SmallArgs p)
 						v1 = s1max ? red3x3<MASK, true>(iu, im, id, c, p.mask)
 						           : red3x3<MASK, false>(iu, im, id, c, p.mask);
 					}
-					const bool ok = trow && cok[c];
-					t1[u][c] = ok ? v1 : nan;
-					if (OSC) t2[u][c] = ok ? v2 : nan;
+					t1[u][c] = v1;
+					if (OSC) t2[u][c] = v2;
+				}
+				// temporaries outside the image are absent: only the threads on the
+				// image's left / right edge and the rows above / below it have any
+				if (!trow || edge_thread) {
+#pragma unroll
+					for (int c = 0; c < 6; c++)
+						if (!(trow && cok[c])) { t1[u][c] = nan; if (OSC) t2[u][c] = nan; }
 				}
 				if (j >= y0 + 2) {
 					// output row j-2 from temporary rows j-3 (slot u+1), j-2 (slot u+2), j-1 (slot u)
@@ -403,7 +465,8 @@ __global__ void __launch_bounds__(256) k_small_2(SmallArgs p)
 			}
 		}
 	}
-	if (__any_sync(0xffffffffu, negzero) && lane == 0) atomicOr(p.flag, 1);
+#undef FETCH2
+	if (__any_sync(0xffffffffu, negzero == 0x80000000u) && lane == 0) atomicOr(p.flag, 1);
 }
 
 // ---- host side ------------------------------------------------------------------
@@ -472,10 +535,10 @@ int morsi_run_small(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int 
 	// 76 % of the HBM copy rate, 64 rows 72 %, 270 rows 60 %): the CTAs in flight
 	// then sweep the image like a copy does and the re-read halo rows hit in L2;
 	// small images get even shorter marches so that every SM has warps to run.
-	// Two stages: longer marches, the warm-up is 4 rows of two reductions (32 rows measured best).
+	// Two stages: longer marches, the warm-up is 4 rows of two reductions (16 rows measured best: cross opening of the C5 batch 0.84 ms, 32 rows 0.91, 64 rows 0.95).
 	const int gx = (job.w + (128 << wxl) - 1) / (128 << wxl);
 	static const int forced_rpw = getenv("MORSI_SMALL_RPW") ? atoi(getenv("MORSI_SMALL_RPW")) : 0;
-	int rpw = plan.stages == 1 ? 8 : 32;
+	int rpw = plan.stages == 1 ? 8 : 16;
 	const int min_rpw = plan.stages == 1 ? 2 : 8;
 	while (rpw > min_rpw && (long long)gx * ((job.y_rows + rpw * segs - 1) / (rpw * segs)) * job.planes < 4LL * c->sm_count)
 		rpw /= 2;
