@@ -8,6 +8,7 @@
 #include "dispatch.cuh"
 #include "k_exact.cuh"
 #include "k_tiled.cuh"
+#include "k_line.cuh"
 
 OpPlan morsi_op_plan(int op)
 {
@@ -74,6 +75,8 @@ struct TiledLaunch {
 	TiledGeom g;
 	int *flag;
 	size_t smem;
+	const LineGeom *line = nullptr;   // non-NULL: the van Herk line kernels (k_line.cuh) instead
+	size_t line_smem = 0;
 };
 
 template <int EPI>
@@ -83,6 +86,30 @@ static int launch_tiled_t(const ExactArgs &a, const TiledLaunch &t, int planes, 
 	if (!attr_set) {
 		cudaFuncSetAttribute(k_tiled_minmax<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 		attr_set = true;
+	}
+	if (t.line) {
+		static bool line_attr_set = false;
+		if (!line_attr_set) {
+			cudaFuncSetAttribute(k_line_minmax<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+			line_attr_set = true;
+		}
+		const LineGeom &g = *t.line;
+		const int per_y = g.vertical ? g.nb * g.L : g.nl;     // output rows per CTA
+		const int per_x = g.vertical ? g.nl : g.nb * g.L;
+		const int blocks_y = (a.y_rows + per_y - 1) / per_y;
+		for (int r0 = 0; r0 < blocks_y; r0 += 65535) {        // gridDim.y limit
+			ExactArgs sub = a;
+			const int nb = blocks_y - r0 < 65535 ? blocks_y - r0 : 65535;
+			sub.y_row0 = a.y_row0 + r0 * per_y;
+			sub.y_rows = a.y_rows - r0 * per_y < (long long)nb * per_y ? a.y_rows - r0 * per_y : nb * per_y;
+			sub.y = a.y + (long long)r0 * per_y * a.w;
+			if (a.y2) sub.y2 = a.y2 + (long long)r0 * per_y * a.w;
+			dim3 grid((a.w + per_x - 1) / per_x, nb, planes);
+			k_line_minmax<EPI><<<grid, 256, t.line_smem, s>>>(sub, g, t.flag);
+			morsi_count_launch(1);
+		}
+		MORSI_CU(cudaGetLastError());
+		return MORSI_OK;
 	}
 	const int rows_y = (a.y_rows + TILED_TY - 1) / TILED_TY;
 	for (int r0 = 0; r0 < rows_y; r0 += 65535) {   // gridDim.y limit
@@ -190,7 +217,7 @@ static int run_minmax_passes(MorsiCtx *c, const DevElement *de, const MorsiJob &
 	a.y = job.y; a.y_pstride = job.y_pstride; a.y_row0 = job.y_row0; a.y_rows = job.y_rows;
 	if (tl) {
 		TiledLaunch t2 = *tl;
-		t2.g.two_tiles = plan.a_from && plan.b_from && a.a_src.p != a.b_src.p;
+		t2.g.two_tiles = !tl->line && plan.a_from && plan.b_from && a.a_src.p != a.b_src.p;
 		if (t2.g.two_tiles) t2.smem += (size_t)t2.g.pw * t2.g.ph * sizeof(float);
 		if (t2.smem > 200 * 1024) return morsi_set_error(MORSI_ERR_INVALID, "tiled: element too large for two tiles");
 		return launch_tiled(plan.epi, a, t2, job.planes, job.stream);
@@ -230,6 +257,49 @@ static int run_exact_chunked(MorsiCtx *c, const DevElement *de, const MorsiJob &
 			int rc = run_minmax_passes(c, de, sub, gate, tl);
 			if (rc) return rc;
 		}
+	return MORSI_OK;
+}
+
+// Long line elements (hrecR / vrecR and any other list that is one contiguous run on a
+// single row or column), length 96 ... 320: van Herk / Gil-Werman, 3 compares per sample
+// whatever the length.  Measured on B200 (4096x4096x3 dilation): 0.6-0.9 ms for every
+// length, against 0.0065 ms x length for k_tiled (hrec150, 299 samples: 0.86 vs 1.92 ms;
+// hrec40, 79 samples: 0.78 vs 0.55 ms), hence the threshold.
+int morsi_run_line(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled)
+{
+	*handled = 0;
+	const OpPlan plan = morsi_op_plan(job.op);
+	const morsi_element_info &in = de->info;
+	if (plan.special || de->n < 96 || de->n > 320 || in.has_duplicates) return MORSI_OK;
+	static const bool off = getenv("MORSI_LINE") && !strcmp(getenv("MORSI_LINE"), "0");
+	if (off) return MORSI_OK;
+	const bool horizontal = in.ymin == in.ymax && in.xmax - in.xmin + 1 == de->n;
+	const bool vertical = in.xmin == in.xmax && in.ymax - in.ymin + 1 == de->n;
+	if (!horizontal && !vertical) return MORSI_OK;
+	LineGeom g;
+	g.vertical = vertical ? 1 : 0;
+	g.L = de->n;
+	g.lo = vertical ? in.ymin : in.xmin;
+	g.perp = vertical ? in.xmin : in.ymin;
+	g.nl = vertical ? 32 : 16;
+	const int cap = vertical ? 256 : 640;                  // outputs per line and CTA (registers, shared memory)
+	g.nb = cap / g.L < 1 ? 1 : cap / g.L;
+	const int len = (g.nb + 1) * g.L;
+	if (vertical) { g.sl = 1; g.sp = 32; }
+	else { g.sp = 1; g.sl = len + ((33 - len % 32) % 32); }   // pitch = 1 (mod 32): the scans of 16 lines hit 16 banks
+	g.two_sources = 0;
+	if ((long long)g.nl * g.nb * g.L > 256LL * LINE_MAXOUT) return MORSI_OK;
+	const size_t tile = (size_t)(vertical ? len * g.sp : g.nl * g.sl) * sizeof(float);
+	if (2 * tile > 200 * 1024) return MORSI_OK;
+	TiledLaunch t;
+	t.g = TiledGeom{};
+	t.flag = flag;
+	t.smem = 0;
+	t.line = &g;
+	t.line_smem = 2 * tile;
+	int rc = run_exact_chunked(c, de, job, nullptr, &t);
+	if (rc) return rc;
+	*handled = 1;
 	return MORSI_OK;
 }
 
@@ -298,11 +368,12 @@ int morsi_dispatch(MorsiCtx *c, const int *e, const MorsiJob &job)
 		if (!handled && !old_march) { rc = morsi_run_disk(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 2; }
 		if (!handled) { rc = morsi_run_march(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 3; }
 		if (!handled) { rc = morsi_run_median(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 4; }
+		if (!handled) { rc = morsi_run_line(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 7; }
 		if (!handled) { rc = morsi_run_tiled(c, de, job, flag, &handled); if (rc) return rc; if (handled == 1) handled = 5; }
 		if (getenv("MORSI_CUDA_TRACE"))
 			fprintf(stderr, "morsi_cuda: op %d n=%d %dx%dx%d rows [%d,+%d): %s\n", job.op, de->n, job.w, job.h, job.planes,
 				job.y_row0, job.y_rows, handled == 1 ? "small" : handled == 2 ? "disk" : handled == 3 ? "march (old)" :
-				handled == 4 ? "median" : handled == 5 ? "tiled" : handled == 6 ? "tiled rank" : "exact only");
+				handled == 4 ? "median" : handled == 5 ? "tiled" : handled == 6 ? "tiled rank" : handled == 7 ? "line (van Herk)" : "exact only");
 		if (handled == 6) return MORSI_OK;             // rank from tiles is exact as it stands
 		if (handled)
 			return path == 2 ? MORSI_OK : run_exact_chunked(c, de, job, flag);

@@ -77,6 +77,7 @@ int morsi_run_disk(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *
 int morsi_run_march(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_median(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_tiled(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
+int morsi_run_line(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 
 #define MORSI_CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
 	return morsi_set_error(e_ == cudaErrorMemoryAllocation ? MORSI_ERR_OOM : MORSI_ERR_CUDA, \

@@ -21,6 +21,7 @@ struct SmallArgs {
 	float *y;
 	long long y_pstride;
 	int y_row0, y_rows;
+	int x_rows;         // rows the band x holds: [x.row0, x.row0 + x_rows); no other row may be read
 	int w, h;
 	unsigned mask;      // bit (dy+1)*3+(dx+1)
 	int rows_per_warp;
@@ -92,9 +93,9 @@ struct RawRow {
 // fetch1 below for what a predicated load into a NaN-initialised register costs.
 template <int HALO, bool VEC>
 __device__ __forceinline__ void fetch_row(const float *plane, int row0, int w, int h,
-		int j, int x0, int lane, RawRow<HALO> &r)
+		int j, int x0, int lane, RawRow<HALO> &r, int row_lo = 0, int row_hi = 0x7fffffff)
 {
-	const bool rowok = j >= 0 && j < h;
+	const bool rowok = j >= 0 && j < h && j >= row_lo && j <= row_hi;   // in the image AND held by the band
 	const float *row = plane + (long long)(j - row0) * w;
 	if (VEC) {
 		const bool cok = rowok && x0 < w;
@@ -178,13 +179,15 @@ struct FetchCtx {
 	const float *pe[HALO];    // its edge columns (lanes 0 / 31), or a dummy
 	unsigned colbits;         // RawRow::ok of a row that exists
 	int row0, h, w;
+	int row_lo, row_hi;       // rows of the image held by the band
 };
 
 template <int HALO>
-__device__ __forceinline__ FetchCtx<HALO> fetch_ctx(const float *plane, int row0, int w, int h, int x0, int lane)
+__device__ __forceinline__ FetchCtx<HALO> fetch_ctx(const float *plane, int row0, int x_rows, int w, int h, int x0, int lane)
 {
 	FetchCtx<HALO> f;
 	f.row0 = row0; f.h = h; f.w = w;
+	f.row_lo = max(0, row0); f.row_hi = min(h, row0 + x_rows) - 1;
 	const bool cok = x0 < w;
 	f.pc = plane + (cok ? x0 : 0);
 	f.colbits = cok ? 1u : 0u;
@@ -198,11 +201,12 @@ __device__ __forceinline__ FetchCtx<HALO> fetch_ctx(const float *plane, int row0
 	return f;
 }
 
-// row j of the image; rows outside it load the nearest row (always inside the band) and are marked absent
+// row j of the image; rows outside the image -- or outside the band: by the caller's contract
+// no element offset reaches those -- load the nearest held row and are marked absent
 template <int HALO>
 __device__ __forceinline__ void fetch_row_vec(const FetchCtx<HALO> &f, int j, RawRow<HALO> &r)
 {
-	const int jc = min(max(j, 0), f.h - 1);
+	const int jc = min(max(j, f.row_lo), f.row_hi);
 	const long long off = (long long)(jc - f.row0) * f.w;
 	const float4 q = __ldg(reinterpret_cast<const float4 *>(f.pc + off));
 	r.c[0] = q.x; r.c[1] = q.y; r.c[2] = q.z; r.c[3] = q.w;
@@ -319,7 +323,10 @@ __global__ void __launch_bounds__(256) k_small_1(SmallArgs p)
 	// input rows j = y0-1 .. y1; window slot of row j is (j-(y0-1)) % 3, its
 	// prefetch slot (j-(y0-1)) % PF; rows are fetched PF ahead, never below
 	// row y1 (the source band may end there)
-#define ROW_OK(j) ((unsigned)(j) < (unsigned)h && (j) <= y1)
+	// rows of the image that the band holds and this warp needs (an element without a
+	// row above / below makes the caller's band end at the output rows: SURVEY 8e)
+	const int row_lo = max(0, p.x.row0), row_hi = min(min(h, p.x.row0 + p.x_rows) - 1, y1);
+#define ROW_OK(j) ((j) >= row_lo && (j) <= row_hi)
 #pragma unroll
 	for (int k = 0; k < PF; k++) {
 		fetch1<VEC>(fp, dummy, ROW_OK(fj), col_ok, edge_ok, eoff, w, x0, raw[k]);
@@ -395,9 +402,9 @@ __global__ void __launch_bounds__(256, OSC ? 2 : 3) k_small_2(SmallArgs p)
 	// temporary row t = j-1 becomes available after loading row j; slot (t-(y0-1)) % 3
 	// output row t-1 = j-2 after temporary rows j-3, j-2, j-1 exist
 	RawRow<2> raw[SMALL_PF];
-	const FetchCtx<2> fc = fetch_ctx<2>(xp, p.x.row0, p.w, p.h, x0, lane);
+	const FetchCtx<2> fc = fetch_ctx<2>(xp, p.x.row0, p.x_rows, p.w, p.h, x0, lane);
 #define FETCH2(j, slot) do { if (VEC) fetch_row_vec<2>(fc, (j), slot); \
-		else fetch_row<2, VEC>(xp, p.x.row0, p.w, p.h, (j), x0, lane, slot); } while (0)
+		else fetch_row<2, VEC>(xp, p.x.row0, p.w, p.h, (j), x0, lane, slot, fc.row_lo, fc.row_hi); } while (0)
 #pragma unroll
 	for (int k = 0; k < SMALL_PF; k++)
 		FETCH2(y0 - 2 + k, raw[k]);
@@ -515,6 +522,7 @@ int morsi_run_small(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int 
 	SmallArgs a;
 	a.x = Band{job.x, job.x_row0, job.x_pstride};
 	a.y = job.y; a.y_pstride = job.y_pstride; a.y_row0 = job.y_row0; a.y_rows = job.y_rows;
+	a.x_rows = job.x_rows;
 	a.w = job.w; a.h = job.h; a.mask = de->info.mask3x3; a.epi = plan.epi; a.flag = flag;
 	a.stage1_min = plan.t_min; a.stage1_max = plan.t_max;
 	a.need_a = plan.a_from != 0; a.need_b = plan.b_from != 0;

@@ -25,15 +25,20 @@ struct TiledGeom {
 #define TILED_TX 128
 #define TILED_TY 16
 
+// gy_lo .. gy_hi: the rows the outputs of this LAUNCH can need.  A band holds
+// exactly those (its caller's contract); the last tile of a launch reaches
+// further down, and those rows -- used only by outputs that are not stored --
+// must not be read.
 __device__ __forceinline__ void tiled_load(float *tile, const Band &src, int plane, int w, int h,
-		int gx0, int gy0, int pw, int ph, int tid, bool &negzero)
+		int gx0, int gy0, int pw, int ph, int tid, bool &negzero, int gy_lo, int gy_hi)
 {
 	const float *sp = src.p + plane * src.pstride;
+	gy_lo = max(gy_lo, 0); gy_hi = min(gy_hi, h - 1);
 	for (int t = tid; t < pw * ph; t += 256) {
 		const int r = t / pw, cc = t - r * pw;
 		const int gx = gx0 + cc, gy = gy0 + r;
 		float v = CUDART_NAN_F;
-		if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+		if (gx >= 0 && gx < w && gy >= gy_lo && gy <= gy_hi) {
 			v = __ldg(sp + (long long)(gy - src.row0) * w + gx);
 			negzero |= __float_as_uint(v) == 0x80000000u;
 		}
@@ -56,8 +61,9 @@ __global__ void __launch_bounds__(256) k_tiled_minmax(ExactArgs p, TiledGeom g, 
 
 	bool negzero = false;
 	const int gx0 = bx + g.xmin, gy0 = p.y_row0 + by + g.ymin;
-	if (NA || !g.two_tiles) tiled_load(tile_a, NA ? p.a_src : p.b_src, plane, p.w, p.h, gx0, gy0, pw, ph, tid, negzero);
-	if (NB && g.two_tiles) tiled_load(tile_b, p.b_src, plane, p.w, p.h, gx0, gy0, pw, ph, tid, negzero);
+	const int need_lo = p.y_row0 + g.ymin, need_hi = p.y_row0 + p.y_rows - 1 + g.ymax;
+	if (NA || !g.two_tiles) tiled_load(tile_a, NA ? p.a_src : p.b_src, plane, p.w, p.h, gx0, gy0, pw, ph, tid, negzero, need_lo, need_hi);
+	if (NB && g.two_tiles) tiled_load(tile_b, p.b_src, plane, p.w, p.h, gx0, gy0, pw, ph, tid, negzero, need_lo, need_hi);
 	for (int k = tid; k < p.n; k += 256) offs[k] = g.tile_offs[k];
 	if (__syncthreads_or(negzero) && tid == 0) atomicOr(flag, 1);
 
@@ -113,7 +119,8 @@ __global__ void __launch_bounds__(256) k_tiled_rank(MedianArgs p, TiledGeom g)
 	float *tile = tiled_smem;
 	int *offs = reinterpret_cast<int *>(tiled_smem + pw * ph);
 	bool unused = false;
-	tiled_load(tile, p.x_src, plane, p.w, p.h, bx + g.xmin, p.y_row0 + by + g.ymin, pw, ph, tid, unused);
+	tiled_load(tile, p.x_src, plane, p.w, p.h, bx + g.xmin, p.y_row0 + by + g.ymin, pw, ph, tid, unused,
+		p.y_row0 + g.ymin, p.y_row0 + p.y_rows - 1 + g.ymax);
 	for (int k = tid; k < p.n; k += 256) offs[k] = g.tile_offs[k];
 	__syncthreads();
 
@@ -124,7 +131,8 @@ __global__ void __launch_bounds__(256) k_tiled_rank(MedianArgs p, TiledGeom g)
 #pragma unroll
 		for (int c = 0; c < 4; c++) {
 			// outside the image u is NaN and every comparison fails; those outputs are not stored anyway
-			u[r][c] = band_pixel(p.x_src, plane, p.w, p.h, bx + tx + 32 * c, p.y_row0 + by + ty + 8 * r);
+			u[r][c] = by + ty + 8 * r < p.y_rows ?
+				band_pixel(p.x_src, plane, p.w, p.h, bx + tx + 32 * c, p.y_row0 + by + ty + 8 * r) : CUDART_NAN_F;
 			cnt[r][c] = 0;
 		}
 	const float *q = tile + ty * pw + tx;

@@ -14,7 +14,7 @@ from oracle import OPS, oracle                 # noqa: E402
 
 ELEMENTS = ["cross", "square", "disk2.5", "disk3", "disk3.5", "disk4", "disk4.2", "disk5", "disk5.1", "disk6", "disk7",
             "disk8", "disk9", "disk10", "disk11", "disk12", "disk13", "disk14", "disk15", "disk6.5", "disk16",
-            "dysk3", "dysk5", "dysk8", "hrec2", "hrec7", "hrec33", "vrec2", "vrec9", "vrec30", "drec5", "Drec6"]
+            "dysk3", "dysk5", "dysk8", "hrec2", "hrec7", "hrec33", "hrec60", "vrec2", "vrec9", "vrec30", "vrec55", "drec5", "Drec6"]
 
 
 def same(a, b):

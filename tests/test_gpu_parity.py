@@ -138,6 +138,19 @@ def test_median_fast_kernels(quad, monkeypatch):
             assert_same(M.apply("median", e, x), o.apply("median", e, x), f"{name} median {w}x{h} quad={quad}")
 
 
+def test_long_lines_van_herk():
+    """hrec / vrec long enough for the van Herk / Gil-Werman kernels (k_line.cuh), also as a
+    user list with an off-centre line, on ragged sizes with NaN / Inf / +-0 sprinkled in"""
+    o = oracle()
+    for (h, w) in [(120, 333), (401, 96), (64, 700)]:
+        x = np.stack([M.synth_host(w, h, plane=p, seed=81, dist=2 if p == 1 else 0) for p in range(2)])
+        x[0][x[0] == 0] = 0.0
+        shifted = np.array([100, 0, 0, 0] + [v for k in range(100) for v in (k - 30, 2)], dtype=np.int32)   # a row line at dy = 2
+        for e in (o.element("hrec50"), o.element("vrec60"), o.element("hrec150"), shifted):
+            for op in ("erosion", "dilation", "opening", "tophat", "gradient", "oscillation", "cblur"):
+                assert_same(M.apply(op, e, x), o.apply(op, e, x), f"line n={e[0]} {op} {w}x{h}")
+
+
 def test_all_nan_windows_and_constant_images():
     """windows with no usable neighbour give +-INF (src/morsi.c:63,77), also on the fast paths"""
     o = oracle()
