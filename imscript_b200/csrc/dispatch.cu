@@ -360,10 +360,10 @@ int morsi_dispatch(MorsiCtx *c, const int *e, const MorsiJob &job)
 		// holds a -0.0, and the order-preserving kernels (no-ops while the
 		// flag is clear) then redo the job
 		int *flag = c->d_flag + job.lane;
-		MORSI_CU(cudaMemsetAsync(flag, 0, sizeof(int), job.stream));
 		int handled = 0;
-		rc = morsi_run_small(c, de, job, flag, &handled);
+		rc = morsi_run_small(c, de, job, flag, &handled);   // clears the flag itself when its kernel uses it
 		if (rc) return rc;
+		if (!handled) MORSI_CU(cudaMemsetAsync(flag, 0, sizeof(int), job.stream));
 		static const bool old_march = getenv("MORSI_DISK") && !strcmp(getenv("MORSI_DISK"), "0");
 		if (!handled && !old_march) { rc = morsi_run_disk(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 2; }
 		if (!handled) { rc = morsi_run_march(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 3; }
@@ -373,8 +373,8 @@ int morsi_dispatch(MorsiCtx *c, const int *e, const MorsiJob &job)
 		if (getenv("MORSI_CUDA_TRACE"))
 			fprintf(stderr, "morsi_cuda: op %d n=%d %dx%dx%d rows [%d,+%d): %s\n", job.op, de->n, job.w, job.h, job.planes,
 				job.y_row0, job.y_rows, handled == 1 ? "small" : handled == 2 ? "disk" : handled == 3 ? "march (old)" :
-				handled == 4 ? "median" : handled == 5 ? "tiled" : handled == 6 ? "tiled rank" : handled == 7 ? "line (van Herk)" : "exact only");
-		if (handled == 6) return MORSI_OK;             // rank from tiles is exact as it stands
+				handled == 4 ? "median" : handled == 5 ? "tiled" : handled == 6 ? "complete in one pass (3x3 with in-kernel signed zeros / tiled rank)" : handled == 7 ? "line (van Herk)" : "exact only");
+		if (handled == 6) return MORSI_OK;             // exact as it stands: tiled rank, 3x3 with in-kernel signed zeros
 		if (handled)
 			return path == 2 ? MORSI_OK : run_exact_chunked(c, de, job, flag);
 	}

@@ -22,6 +22,7 @@ struct RowRunPlan {
 struct DevElement {
 	int n;
 	int2 *d_offs;                 // effective offsets, element order, on the device
+	int canonical3x3;             // the list IS the reference's cross (1) / square = disk2 (2) literal, in its order
 	int *d_tile_offs;             // k_tiled: (dy-ymin)*pw + (dx-xmin) per element, pw = 128 + xmax - xmin
 	morsi_element_info info;
 	RowRunPlan rowrun;

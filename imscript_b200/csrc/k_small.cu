@@ -13,6 +13,7 @@
 // seen in the loaded data raises *flag and the dispatcher re-runs the
 // order-preserving kernels.
 #include <cstdlib>
+#include <cstring>
 
 #include "dispatch.cuh"
 
@@ -26,6 +27,8 @@ struct SmallArgs {
 	unsigned mask;      // bit (dy+1)*3+(dx+1)
 	int rows_per_warp;
 	int wx_log2;        // k_small_1: 2^wx_log2 warps of a CTA sit side by side on the same rows
+	int inline_exact;   // k_small_1, canonical cross / square lists: warps that meet a -0.0 switch to the
+	                    // order-preserving reduction themselves; no flag, no gated re-run
 	int epi;            // Epi
 	int stage1_min, stage1_max;   // two-stage: which temporaries exist
 	int need_a, need_b;           // final pass: erosion side / dilation side
@@ -52,6 +55,26 @@ __device__ __forceinline__ float red3x3(const float (&up)[N], const float (&mid)
 		if (m & (1u << (3 + dx))) r = mm<ISMAX>(r, mid[c + dx]);
 		if (m & (1u << (6 + dx))) r = mm<ISMAX>(r, dn[c + dx]);
 	}
+	return r;
+}
+
+// The same reduction in the REFERENCE's element order with its tie rule (glibc
+// fmin/fmax return the later operand on ties, so the last occurrence of the
+// extremum wins: SURVEY.md 9.1-Z) -- only +0/-0 can tell the difference.  Lists
+// in canonical order only: cross = (-1,0),(0,0),(1,0),(0,-1),(0,1) (src/morsi.c:484),
+// square / disk2 = dx outer, dy inner (src/morsi.c:485, 319-320).
+template <int MASK, bool ISMAX, int N>
+__device__ __forceinline__ float red3x3_exact(const float (&up)[N], const float (&mid)[N], const float (&dn)[N], int c)
+{
+	float r = ISMAX ? -CUDART_INF_F : CUDART_INF_F;
+#define STEP(v) do { const float t_ = (v); r = ISMAX ? (t_ >= r ? t_ : r) : (t_ <= r ? t_ : r); } while (0)
+	if (MASK == 0272) {
+		STEP(mid[c]); STEP(mid[c + 1]); STEP(mid[c + 2]); STEP(up[c + 1]); STEP(dn[c + 1]);
+	} else {
+#pragma unroll
+		for (int dx = 0; dx < 3; dx++) { STEP(up[c + dx]); STEP(mid[c + dx]); STEP(dn[c + dx]); }
+	}
+#undef STEP
 	return r;
 }
 
@@ -306,6 +329,7 @@ __global__ void __launch_bounds__(256) k_small_1(SmallArgs p)
 	constexpr bool CT = EPI >= 0;
 	const bool need_a = CT ? EpiNeeds<CT ? EPI : 0>::a : (p.need_a != 0);
 	const bool need_b = CT ? EpiNeeds<CT ? EPI : 0>::b : (p.need_b != 0);
+	const bool inl = (MASK == 0272 || MASK == 0777) && p.inline_exact != 0;
 
 	// running pointers: next row to fetch, next row to store
 	const float *dummy = p.x.p + plane * p.x.pstride;          // always readable, 16-byte aligned
@@ -351,11 +375,18 @@ __global__ void __launch_bounds__(256) k_small_1(SmallArgs p)
 				const float (&mid)[6] = in[(u + 1) % 3];
 				const float (&dn)[6] = in[(u + 2) % 3];
 				float o[4];
+				// a warp that has met a -0.0 reduces in the reference's order from then on
+				const bool slow = inl && __any_sync(0xffffffffu, negzero == 0x80000000u);
 #pragma unroll
 				for (int c = 0; c < 4; c++) {
 					float a = 0.f, b = 0.f;
-					if (need_a) a = red3x3<MASK, false>(up, mid, dn, c, p.mask);
-					if (need_b) b = red3x3<MASK, true>(up, mid, dn, c, p.mask);
+					if (slow) {
+						if (need_a) a = red3x3_exact<(MASK == 0272 ? 0272 : 0777), false>(up, mid, dn, c);
+						if (need_b) b = red3x3_exact<(MASK == 0272 ? 0272 : 0777), true>(up, mid, dn, c);
+					} else {
+						if (need_a) a = red3x3<MASK, false>(up, mid, dn, c, p.mask);
+						if (need_b) b = red3x3<MASK, true>(up, mid, dn, c, p.mask);
+					}
 					o[c] = CT ? epilogue<CT ? EPI : 0>(a, b, mid[c + 1]) : apply_epi(p.epi, a, b, mid[c + 1]);
 				}
 				if (VEC) { if (col_ok) *reinterpret_cast<float4 *>(yq) = make_float4(o[0], o[1], o[2], o[3]); }
@@ -365,7 +396,7 @@ __global__ void __launch_bounds__(256) k_small_1(SmallArgs p)
 		}
 	}
 #undef ROW_OK
-	if (__any_sync(0xffffffffu, negzero == 0x80000000u) && lane == 0) atomicOr(p.flag, 1);
+	if (!inl && __any_sync(0xffffffffu, negzero == 0x80000000u) && lane == 0) atomicOr(p.flag, 1);
 }
 
 // ---- two stages fused ---------------------------------------------------------
@@ -555,6 +586,11 @@ int morsi_run_small(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int 
 	dim3 block(32, 8);
 	dim3 grid(gx, (job.y_rows + rpw * segs - 1) / (rpw * segs), job.planes);
 	const unsigned CROSS = 0272u /* .#. ### .#. */, SQUARE = 0777u;
+	// single stage over a canonical cross / square list: the kernel resolves signed zeros itself
+	static const bool no_inline = getenv("MORSI_SMALL_INLINE") && !strcmp(getenv("MORSI_SMALL_INLINE"), "0");
+	a.inline_exact = vec && plan.stages == 1 && !no_inline &&
+		((a.mask == CROSS && de->canonical3x3 == 1) || (a.mask == SQUARE && de->canonical3x3 == 2));
+	if (!a.inline_exact) MORSI_CU(cudaMemsetAsync(flag, 0, sizeof(int), job.stream));
 	if (vec) {
 		if (a.mask == CROSS) launch_small_t<(int)0272, true>(a, plan.stages, osc, grid, block, job.stream);
 		else if (a.mask == SQUARE) launch_small_t<(int)0777, true>(a, plan.stages, osc, grid, block, job.stream);
@@ -564,6 +600,6 @@ int morsi_run_small(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int 
 	}
 	morsi_count_launch(1);
 	MORSI_CU(cudaGetLastError());
-	*handled = 1;
+	*handled = a.inline_exact ? 6 : 1;                 // 6: complete, no gated re-run
 	return MORSI_OK;
 }

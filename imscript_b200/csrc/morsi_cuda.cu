@@ -203,6 +203,20 @@ int morsi_element_get(MorsiCtx *c, const int *e, const DevElement **out)
 		offs[k] = make_int2(e[4 + 2*k] - e[2], e[5 + 2*k] - e[3]);
 	CU(cudaMalloc(&d.d_offs, ((size_t)d.n + 1) * sizeof(int2)));
 	CU(cudaMemcpy(d.d_offs, offs.data(), ((size_t)d.n + 1) * sizeof(int2), cudaMemcpyHostToDevice));
+	// the reference's own 3x3 literals, in their order (src/morsi.c:484-485; disk2 builds the square's list)
+	{
+		static const int cross[5][2] = {{-1, 0}, {0, 0}, {1, 0}, {0, -1}, {0, 1}};
+		d.canonical3x3 = 0;
+		if (d.n == 5) {
+			bool same = true;
+			for (int k = 0; k < 5; k++) same &= offs[k].x == cross[k][0] && offs[k].y == cross[k][1];
+			if (same) d.canonical3x3 = 1;
+		} else if (d.n == 9) {
+			bool same = true;
+			for (int k = 0; k < 9; k++) same &= offs[k].x == k / 3 - 1 && offs[k].y == k % 3 - 1;
+			if (same) d.canonical3x3 = 2;
+		}
+	}
 	// k_tiled: offsets into a shared-memory tile of pitch 128 + (xmax - xmin)
 	d.d_tile_offs = nullptr;
 	if (d.n > 0 && d.n <= 8192) {
