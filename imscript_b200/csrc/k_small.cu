@@ -13,6 +13,7 @@
 // seen in the loaded data raises *flag and the dispatcher re-runs the
 // order-preserving kernels.
 #include <cstdlib>
+#include <type_traits>
 #include <cstring>
 
 #include "dispatch.cuh"
@@ -76,6 +77,17 @@ __device__ __forceinline__ float red3x3_exact(const float (&up)[N], const float 
 	}
 #undef STEP
 	return r;
+}
+
+// fast reduction, or the order-preserving one once the warp has met a -0.0 (canonical lists only)
+template <int MASK, bool ISMAX, int N>
+__device__ __forceinline__ float red3x3_sel(bool slow, const float (&up)[N], const float (&mid)[N],
+		const float (&dn)[N], int c, unsigned rmask)
+{
+	if (MASK == 0272 || MASK == 0777) {
+		if (slow) return red3x3_exact<(MASK == 0272 ? 0272 : 0777), ISMAX>(up, mid, dn, c);
+	}
+	return red3x3<MASK, ISMAX>(up, mid, dn, c, rmask);
 }
 
 __device__ __forceinline__ float apply_epi(int epi, float a, float b, float x)
@@ -407,6 +419,7 @@ __global__ void __launch_bounds__(256, OSC ? 2 : 3) k_small_2(SmallArgs p)
 {
 	const bool s1max = S1 < 0 ? p.stage1_max != 0 : S1 == 1;
 	constexpr bool CT = EPI >= 0;
+	const bool inl = (MASK == 0272 || MASK == 0777) && p.inline_exact != 0;
 	const int lane = threadIdx.x;
 	const int x0 = (blockIdx.x * 32 + lane) * 4;
 	const int plane = blockIdx.z;
@@ -454,57 +467,63 @@ __global__ void __launch_bounds__(256, OSC ? 2 : 3) k_small_2(SmallArgs p)
 				const float (&iu)[8] = in[u % 3];
 				const float (&im)[8] = in[(u + 1) % 3];
 				const float (&id)[8] = in[(u + 2) % 3];
-				// temporary row t = j-1 -> slot u
-				const int t = j - 1;
-				const bool trow = t >= 0 && t < p.h;
+				// temporary row t = j-1 -> slot u; output row j-2 from temporary rows j-3 (slot u+1),
+				// j-2 (slot u+2), j-1 (slot u).  SLOW: the reference's element order (a warp that has
+				// met a -0.0 reduces both stages that way from then on); one branch per row, two bodies.
+				auto row_body = [&](auto slow_c) {
+					constexpr bool SLOW = decltype(slow_c)::value;
+					const int t = j - 1;
+					const bool trow = t >= 0 && t < p.h;
 #pragma unroll
-				for (int c = 0; c < 6; c++) {
-					float v1, v2 = nan;
-					if (OSC) {
-						v1 = red3x3<MASK, false>(iu, im, id, c, p.mask);
-						v2 = red3x3<MASK, true>(iu, im, id, c, p.mask);
-					} else {
-						v1 = s1max ? red3x3<MASK, true>(iu, im, id, c, p.mask)
-						           : red3x3<MASK, false>(iu, im, id, c, p.mask);
-					}
-					t1[u][c] = v1;
-					if (OSC) t2[u][c] = v2;
-				}
-				// temporaries outside the image are absent: only the threads on the
-				// image's left / right edge and the rows above / below it have any
-				if (!trow || edge_thread) {
-#pragma unroll
-					for (int c = 0; c < 6; c++)
-						if (!(trow && cok[c])) { t1[u][c] = nan; if (OSC) t2[u][c] = nan; }
-				}
-				if (j >= y0 + 2) {
-					// output row j-2 from temporary rows j-3 (slot u+1), j-2 (slot u+2), j-1 (slot u)
-					const float (&tu)[6] = t1[(u + 1) % 3];
-					const float (&tm)[6] = t1[(u + 2) % 3];
-					const float (&td)[6] = t1[u % 3];
-					float o[4];
-#pragma unroll
-					for (int c = 0; c < 4; c++) {
-						float a = 0.f, b = 0.f;
+					for (int c = 0; c < 6; c++) {
+						float v1, v2 = nan;
 						if (OSC) {
-							// closing - opening: A = min over dilation, B = max over erosion
-							a = red3x3<MASK, false>(t2[(u + 1) % 3], t2[(u + 2) % 3], t2[u % 3], c, p.mask);
-							b = red3x3<MASK, true>(tu, tm, td, c, p.mask);
-						} else if (s1max) {
-							a = red3x3<MASK, false>(tu, tm, td, c, p.mask);
+							v1 = red3x3_sel<MASK, false>(SLOW, iu, im, id, c, p.mask);
+							v2 = red3x3_sel<MASK, true>(SLOW, iu, im, id, c, p.mask);
 						} else {
-							b = red3x3<MASK, true>(tu, tm, td, c, p.mask);
+							v1 = s1max ? red3x3_sel<MASK, true>(SLOW, iu, im, id, c, p.mask)
+							           : red3x3_sel<MASK, false>(SLOW, iu, im, id, c, p.mask);
 						}
-						// x at row j-2: input slot of row j-2 is u % 3, columns offset by 2
-						o[c] = CT ? epilogue<CT ? EPI : 0>(a, b, iu[c + 2]) : apply_epi(p.epi, a, b, iu[c + 2]);
+						t1[u][c] = v1;
+						if (OSC) t2[u][c] = v2;
 					}
-					store_row<VEC>(yp + (long long)(j - 2 - p.y_row0) * p.w, x0, p.w, o);
-				}
+					// temporaries outside the image are absent: only the threads on the
+					// image's left / right edge and the rows above / below it have any
+					if (!trow || edge_thread) {
+#pragma unroll
+						for (int c = 0; c < 6; c++)
+							if (!(trow && cok[c])) { t1[u][c] = nan; if (OSC) t2[u][c] = nan; }
+					}
+					if (j >= y0 + 2) {
+						const float (&tu)[6] = t1[(u + 1) % 3];
+						const float (&tm)[6] = t1[(u + 2) % 3];
+						const float (&td)[6] = t1[u % 3];
+						float o[4];
+#pragma unroll
+						for (int c = 0; c < 4; c++) {
+							float a = 0.f, b = 0.f;
+							if (OSC) {
+								// closing - opening: A = min over dilation, B = max over erosion
+								a = red3x3_sel<MASK, false>(SLOW, t2[(u + 1) % 3], t2[(u + 2) % 3], t2[u % 3], c, p.mask);
+								b = red3x3_sel<MASK, true>(SLOW, tu, tm, td, c, p.mask);
+							} else if (s1max) {
+								a = red3x3_sel<MASK, false>(SLOW, tu, tm, td, c, p.mask);
+							} else {
+								b = red3x3_sel<MASK, true>(SLOW, tu, tm, td, c, p.mask);
+							}
+							// x at row j-2: input slot of row j-2 is u % 3, columns offset by 2
+							o[c] = CT ? epilogue<CT ? EPI : 0>(a, b, iu[c + 2]) : apply_epi(p.epi, a, b, iu[c + 2]);
+						}
+						store_row<VEC>(yp + (long long)(j - 2 - p.y_row0) * p.w, x0, p.w, o);
+					}
+				};
+				if (inl && __any_sync(0xffffffffu, negzero == 0x80000000u)) row_body(std::true_type());
+				else row_body(std::false_type());
 			}
 		}
 	}
 #undef FETCH2
-	if (__any_sync(0xffffffffu, negzero == 0x80000000u) && lane == 0) atomicOr(p.flag, 1);
+	if (!inl && __any_sync(0xffffffffu, negzero == 0x80000000u) && lane == 0) atomicOr(p.flag, 1);
 }
 
 // ---- host side ------------------------------------------------------------------
@@ -586,9 +605,9 @@ int morsi_run_small(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int 
 	dim3 block(32, 8);
 	dim3 grid(gx, (job.y_rows + rpw * segs - 1) / (rpw * segs), job.planes);
 	const unsigned CROSS = 0272u /* .#. ### .#. */, SQUARE = 0777u;
-	// single stage over a canonical cross / square list: the kernel resolves signed zeros itself
+	// a canonical cross / square list: the kernels resolve signed zeros themselves
 	static const bool no_inline = getenv("MORSI_SMALL_INLINE") && !strcmp(getenv("MORSI_SMALL_INLINE"), "0");
-	a.inline_exact = vec && plan.stages == 1 && !no_inline &&
+	a.inline_exact = vec && !no_inline &&
 		((a.mask == CROSS && de->canonical3x3 == 1) || (a.mask == SQUARE && de->canonical3x3 == 2));
 	if (!a.inline_exact) MORSI_CU(cudaMemsetAsync(flag, 0, sizeof(int), job.stream));
 	if (vec) {
