@@ -367,6 +367,7 @@ int morsi_dispatch(MorsiCtx *c, const int *e, const MorsiJob &job)
 		static const bool old_march = getenv("MORSI_DISK") && !strcmp(getenv("MORSI_DISK"), "0");
 		if (!handled && !old_march) { rc = morsi_run_disk(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 2; }
 		if (!handled) { rc = morsi_run_march(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 3; }
+		if (!handled) { rc = morsi_run_median3(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 4; }
 		if (!handled) { rc = morsi_run_median(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 4; }
 		if (!handled) { rc = morsi_run_line(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 7; }
 		if (!handled) { rc = morsi_run_tiled(c, de, job, flag, &handled); if (rc) return rc; if (handled == 1) handled = 5; }

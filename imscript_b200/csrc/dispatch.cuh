@@ -77,6 +77,7 @@ int morsi_run_small(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int 
 int morsi_run_disk(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_march(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_median(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
+int morsi_run_median3(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_tiled(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_line(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 

@@ -622,3 +622,180 @@ int morsi_run_small(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int 
 	*handled = a.inline_exact ? 6 : 1;                 // 6: complete, no gated re-run
 	return MORSI_OK;
 }
+
+// ---- 3x3 median (src/morsi.c:91-120 over cross / square = disk2) ----------------------------
+// The same row march as k_small_1: 4 columns per thread, 3-row register window,
+// unconditional prefetch.  A window whose samples are all finite (the usual
+// case) goes through a sorting network of which only the middle output is
+// live (25 comparators for 9 samples, 9 for 5; verified exhaustively with the
+// 0-1 principle); windows with absent or non-finite samples (image frame,
+// NaN / Inf data: the reference drops them, src/morsi.c:115) sort with +INF
+// stand-ins and pick the reference's variable-count positions (:93-100).
+// Ties of +0 and -0 depend on the reference's stable sort: -0.0 raises *flag
+// and the order-preserving kernel re-runs the job.
+__device__ __forceinline__ void cex3(float &a, float &b)
+{
+	const float lo = fminf(a, b), hi = fmaxf(a, b);
+	a = lo; b = hi;
+}
+template <int N> __device__ __forceinline__ void sort_small(float (&v)[N])
+{
+	if (N == 9) {
+		cex3(v[0], v[3]); cex3(v[1], v[7]); cex3(v[2], v[5]); cex3(v[4], v[8]);
+		cex3(v[0], v[7]); cex3(v[2], v[4]); cex3(v[3], v[8]); cex3(v[5], v[6]);
+		cex3(v[0], v[2]); cex3(v[1], v[3]); cex3(v[4], v[5]); cex3(v[7], v[8]);
+		cex3(v[1], v[4]); cex3(v[3], v[6]); cex3(v[5], v[7]);
+		cex3(v[0], v[1]); cex3(v[2], v[4]); cex3(v[3], v[5]); cex3(v[6], v[8]);
+		cex3(v[2], v[3]); cex3(v[4], v[5]); cex3(v[6], v[7]);
+		cex3(v[1], v[2]); cex3(v[3], v[4]); cex3(v[5], v[6]);
+	} else {
+		cex3(v[0], v[1]); cex3(v[3], v[4]); cex3(v[2], v[4]); cex3(v[2], v[3]); cex3(v[1], v[4]);
+		cex3(v[0], v[3]); cex3(v[0], v[2]); cex3(v[1], v[3]); cex3(v[1], v[2]);
+	}
+}
+template <int N> __device__ __noinline__ float median_small_general(float v0, float v1, float v2, float v3, float v4,
+		float v5, float v6, float v7, float v8)
+{
+	float v[9] = {v0, v1, v2, v3, v4, v5, v6, v7, v8};
+	float s[N];
+	int cnt = 0;
+#pragma unroll
+	for (int i = 0; i < N; i++) { const bool f = isfinite(v[i]); cnt += f; s[i] = f ? v[i] : CUDART_INF_F; }
+	sort_small<N>(s);
+	if (cnt < 1) return CUDART_NAN_F;                                     // src/morsi.c:93
+	const int lo = cnt == 2 ? 0 : cnt / 2;                                // :94 (n == 1), :95 (n == 2), :100 (odd), :98 (even)
+	float a = s[0], b = s[1];
+#pragma unroll
+	for (int i = 1; i < N; i++) { a = i == lo ? s[i] : a; b = i == lo + 1 ? s[i] : b; }
+	return (cnt & 1) ? a : __fmul_rn(__fadd_rn(a, b), 0.5f);
+}
+
+template <int MASK>
+__global__ void __launch_bounds__(256) k_median3(SmallArgs p)
+{
+	constexpr int N = MASK == 0272 ? 5 : 9;
+	constexpr int PF = 3;
+	const int lane = threadIdx.x;
+	const int wxm = (1 << p.wx_log2) - 1;
+	const int x0 = (((blockIdx.x << p.wx_log2) + (threadIdx.y & wxm)) * 32 + lane) * 4;
+	const int plane = blockIdx.z;
+	const int seg = blockIdx.y * (blockDim.y >> p.wx_log2) + (threadIdx.y >> p.wx_log2);
+	const int jj0 = seg * p.rows_per_warp;
+	if (jj0 >= p.y_rows || x0 - 4 * lane >= p.w) return;      // the whole warp: no barrier in this kernel
+	const int jj1 = min(p.y_rows, jj0 + p.rows_per_warp);
+	const int y0 = p.y_row0 + jj0, y1 = p.y_row0 + jj1;
+	const int w = p.w, h = p.h;
+	unsigned negzero = 0;
+
+	const float *dummy = p.x.p + plane * p.x.pstride;
+	const float *fp = dummy + (long long)(y0 - 1 - p.x.row0) * w + x0;
+	int fj = y0 - 1;
+	float *yq = p.y + plane * p.y_pstride + (long long)(y0 - p.y_row0) * w + x0;
+	const bool col_ok = x0 < w;
+	const int eoff = lane == 0 ? -1 : 4;
+	const bool edge_ok = (lane == 0 && x0 > 0 && x0 - 1 < w) || (lane == 31 && x0 + 4 < w);
+
+	float in[3][6];
+	bool fin[3];            // every sample of the row's 6 columns is finite
+	Raw1 raw[PF];
+	const int row_lo = max(0, p.x.row0), row_hi = min(min(h, p.x.row0 + p.x_rows) - 1, y1);
+#define ROW_OK(j) ((j) >= row_lo && (j) <= row_hi)
+#define ROW_FIN(r) (isfinite(r[0]) && isfinite(r[1]) && isfinite(r[2]) && isfinite(r[3]) && isfinite(r[4]) && isfinite(r[5]))
+#pragma unroll
+	for (int k = 0; k < PF; k++) {
+		fetch1<true>(fp, dummy, ROW_OK(fj), col_ok, edge_ok, eoff, w, x0, raw[k]);
+		fp += w; fj++;
+	}
+	assemble1<true>(raw[0], ROW_OK(y0 - 1) && col_ok, ROW_OK(y0 - 1) && edge_ok, lane, in[0], negzero);
+	fin[0] = ROW_FIN(in[0]);
+	fetch1<true>(fp, dummy, ROW_OK(fj), col_ok, edge_ok, eoff, w, x0, raw[0]);
+	fp += w; fj++;
+	assemble1<true>(raw[1], ROW_OK(y0) && col_ok, ROW_OK(y0) && edge_ok, lane, in[1], negzero);
+	fin[1] = ROW_FIN(in[1]);
+	fetch1<true>(fp, dummy, ROW_OK(fj), col_ok, edge_ok, eoff, w, x0, raw[1]);
+	fp += w; fj++;
+	for (int jb = y0 + 1; jb <= y1; jb += PF) {
+#pragma unroll
+		for (int u = 0; u < PF; u++) {
+			const int j = jb + u;               // row slot (u+2)%3
+			if (j <= y1) {
+				const bool rok = ROW_OK(j);
+				assemble1<true>(raw[(u + 2) % PF], rok && col_ok, rok && edge_ok, lane, in[(u + 2) % 3], negzero);
+				fin[(u + 2) % 3] = ROW_FIN(in[(u + 2) % 3]);
+				fetch1<true>(fp, dummy, ROW_OK(fj), col_ok, edge_ok, eoff, w, x0, raw[(u + 2) % PF]);
+				fp += w; fj++;
+				const float (&up)[6] = in[u % 3];
+				const float (&mid)[6] = in[(u + 1) % 3];
+				const float (&dn)[6] = in[(u + 2) % 3];
+				// (a thread on the image frame sees NaN = not finite in its edge columns / rows)
+				const bool clean = fin[0] && fin[1] && fin[2];
+				float o[4];
+#pragma unroll
+				for (int c = 0; c < 4; c++) {
+					float v[9];
+					if (N == 9) {
+						v[0] = up[c]; v[1] = up[c + 1]; v[2] = up[c + 2]; v[3] = mid[c]; v[4] = mid[c + 1];
+						v[5] = mid[c + 2]; v[6] = dn[c]; v[7] = dn[c + 1]; v[8] = dn[c + 2];
+					} else {
+						v[0] = mid[c]; v[1] = mid[c + 1]; v[2] = mid[c + 2]; v[3] = up[c + 1]; v[4] = dn[c + 1];
+						v[5] = 0.f; v[6] = 0.f; v[7] = 0.f; v[8] = 0.f;
+					}
+					if (clean) {
+						float s[N];
+#pragma unroll
+						for (int i = 0; i < N; i++) s[i] = v[i];
+						sort_small<N>(s);
+						o[c] = s[N / 2];
+					} else {
+						o[c] = median_small_general<N>(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8]);
+					}
+				}
+				if (col_ok) *reinterpret_cast<float4 *>(yq) = make_float4(o[0], o[1], o[2], o[3]);
+				yq += w;
+			}
+		}
+	}
+#undef ROW_OK
+#undef ROW_FIN
+	if (__any_sync(0xffffffffu, negzero == 0x80000000u) && lane == 0) atomicOr(p.flag, 1);
+}
+
+// median by the reference's cross / square (= disk2) over 16-byte aligned planes
+int morsi_run_median3(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled)
+{
+	*handled = 0;
+	if (job.op != MORSI_MEDIAN || de->info.kind != MORSI_EK_SMALL || de->info.has_duplicates) return MORSI_OK;
+	static const bool off = getenv("MORSI_MEDIAN3") && !strcmp(getenv("MORSI_MEDIAN3"), "0");
+	if (off) return MORSI_OK;
+	const unsigned CROSS = 0272u, SQUARE = 0777u;
+	const unsigned mask = de->info.mask3x3;
+	if (!((mask == CROSS && de->n == 5) || (mask == SQUARE && de->n == 9))) return MORSI_OK;
+	const bool vec = (job.w % 4 == 0) && (((uintptr_t)job.x) % 16 == 0) && (((uintptr_t)job.y) % 16 == 0)
+		&& (job.x_pstride % 4 == 0) && (job.y_pstride % 4 == 0);
+	if (!vec) return MORSI_OK;
+	SmallArgs a;
+	a.x = Band{job.x, job.x_row0, job.x_pstride};
+	a.y = job.y; a.y_pstride = job.y_pstride; a.y_row0 = job.y_row0; a.y_rows = job.y_rows;
+	a.x_rows = job.x_rows;
+	a.w = job.w; a.h = job.h; a.mask = mask; a.epi = EPI_A; a.flag = flag;
+	a.stage1_min = a.stage1_max = a.need_a = a.need_b = a.a_from_tmax = a.b_from_tmin = 0;
+	a.inline_exact = 0;
+	int wxl = 0;
+	while (wxl < 3 && (128 << (wxl + 1)) <= job.w + 127) wxl++;
+	a.wx_log2 = wxl;
+	const int segs = 8 >> wxl;
+	const int gx = (job.w + (128 << wxl) - 1) / (128 << wxl);
+	int rpw = 8;
+	while (rpw > 2 && (long long)gx * ((job.y_rows + rpw * segs - 1) / (rpw * segs)) * job.planes < 4LL * c->sm_count)
+		rpw /= 2;
+	a.rows_per_warp = rpw;
+	const long long gy = (job.y_rows + rpw * segs - 1) / (rpw * segs);
+	if (gy > 65535 || job.planes > 65535) return MORSI_OK;
+	dim3 block(32, 8), grid(gx, (unsigned)gy, job.planes);
+	if (mask == CROSS) k_median3<0272><<<grid, block, 0, job.stream>>>(a);
+	else k_median3<0777><<<grid, block, 0, job.stream>>>(a);
+	morsi_count_launch(1);
+	MORSI_CU(cudaGetLastError());
+	*handled = 1;
+	return MORSI_OK;
+}

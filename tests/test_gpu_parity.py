@@ -127,7 +127,7 @@ def test_median_fast_kernels(quad, monkeypatch):
     plane (per-pixel general path), and the small 3x3 elements"""
     monkeypatch.setenv("MORSI_MEDIAN_QUAD", quad)
     o = oracle()
-    for (h, w) in [(151, 203), (64, 130), (37, 66)]:
+    for (h, w) in [(151, 203), (64, 130), (37, 66), (75, 260)]:     # 260: the 16-byte aligned 3x3 median kernel
         x = np.stack([M.synth_host(w, h, plane=p, seed=51, dist=p) for p in range(3)])
         x[x == 0] = 0.0
         for name in ["disk2.5", "disk3", "disk3.5", "disk4", "disk4.2", "disk5", "disk5.1", "disk6", "disk7",
