@@ -22,7 +22,12 @@ EXPORTED_SYMBOLS = [
     "morsi_cuda_memcpy_d2h", "morsi_cuda_memcpy_d2d", "morsi_cuda_sync", "morsi_cuda_synth",
     "morsi_synth_host", "morsi_cuda_event_create", "morsi_cuda_event_record",
     "morsi_cuda_event_elapsed_ms", "morsi_cuda_event_destroy",
+    "morsi_shard_create", "morsi_shard_handle", "morsi_shard_connect", "morsi_shard_rows",
+    "morsi_shard_buffer", "morsi_shard_stream", "morsi_shard_apply", "morsi_shard_apply_host",
+    "morsi_shard_exchange", "morsi_cuda_stream_create", "morsi_cuda_stream_destroy",
+    "morsi_shard_sync", "morsi_shard_halo_bytes", "morsi_shard_destroy", "morsi_cuda_apply_sharded",
 ]
+SHARD_HANDLE_BYTES = 128
 COMPAT_SYMBOLS = ["morsi_" + o for o in OPS] + ["morsi_all", "build_disk"]
 
 _f32p = ctypes.POINTER(ctypes.c_float)
@@ -91,6 +96,25 @@ def lib():
         L.morsi_cuda_event_record.argtypes = [_vp, _vp]
         L.morsi_cuda_event_elapsed_ms.argtypes = [_vp, _vp, ctypes.POINTER(ctypes.c_float)]
         L.morsi_cuda_event_destroy.argtypes = [_vp]
+        L.morsi_shard_create.argtypes = [ctypes.POINTER(_vp)] + [ctypes.c_int] * 7
+        L.morsi_shard_handle.argtypes = [_vp, _vp]
+        L.morsi_shard_connect.argtypes = [_vp, _vp]
+        L.morsi_shard_rows.argtypes = [_vp, _i32p, _i32p, _i32p, _i32p]
+        L.morsi_shard_buffer.restype = _vp
+        L.morsi_shard_buffer.argtypes = [_vp, ctypes.c_int]
+        L.morsi_shard_stream.restype = _vp
+        L.morsi_shard_stream.argtypes = [_vp]
+        L.morsi_shard_apply.argtypes = [_vp, ctypes.c_int, _i32p, ctypes.c_int, ctypes.c_int]
+        L.morsi_shard_apply_host.argtypes = [_vp, ctypes.c_int, _i32p, _vp, _vp]
+        L.morsi_shard_sync.argtypes = [_vp]
+        L.morsi_shard_exchange.argtypes = [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.morsi_cuda_stream_create.argtypes = [ctypes.POINTER(_vp)]
+        L.morsi_cuda_stream_destroy.argtypes = [_vp]
+        L.morsi_shard_halo_bytes.restype = ctypes.c_longlong
+        L.morsi_shard_halo_bytes.argtypes = [_vp]
+        L.morsi_shard_destroy.argtypes = [_vp]
+        L.morsi_cuda_apply_sharded.argtypes = [ctypes.c_int, _i32p, _vp, _vp, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_int]
         _lib = L
     return _lib
 
@@ -225,6 +249,17 @@ def apply_band_device(op, e, d_x, x_row0, x_rows, d_y, y_row0, y_rows, w, h, str
                                              py, y_row0, y_rows, w, h, stream))
     if sync:
         check(lib().morsi_cuda_sync(stream))
+
+
+def apply_sharded(op, e, x, ndev, iterations=1):
+    """One process, `ndev` devices: morsi_cuda_apply_sharded() on a (h,w) plane."""
+    e = _e(e)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    h, w = x.shape
+    y = np.empty_like(x)
+    check(lib().morsi_cuda_apply_sharded(_op(op), e.ctypes.data_as(_i32p), x.ctypes.data, y.ctypes.data,
+                                         w, h, ndev, iterations))
+    return y
 
 
 def synth_host(w, rows, row0=0, plane=0, seed=1, dist=0):

@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <mutex>
+
 #include "dispatch.cuh"
 #include "k_exact.cuh"
 #include "k_tiled.cuh"
@@ -46,6 +48,22 @@ void morsi_element_compile(MorsiCtx *, DevElement *d)
 	}
 }
 
+// Opt a kernel in to > 48 KB of dynamic shared memory.  The attribute is per
+// DEVICE: remember (kernel, device) pairs, under a lock (morsi_cuda_apply runs
+// one host thread per device with MORSI_CUDA_DEVICES > 1).
+int morsi_optin_smem(const void *kernel, int device, int bytes)
+{
+	static std::mutex mu;
+	static std::map<const void *, unsigned long long> done;
+	std::lock_guard<std::mutex> lk(mu);
+	unsigned long long &m = done[kernel];
+	const unsigned long long bit = 1ull << (device & 63);
+	if (m & bit) return MORSI_OK;
+	MORSI_CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+	m |= bit;
+	return MORSI_OK;
+}
+
 // Gated launches (re-runs that are no-ops unless a -0.0 was seen) use a small
 // grid-stride grid so that the usual no-op costs a few microseconds.
 static dim3 exact_grid(int w, int rows, int planes, bool gated)
@@ -80,19 +98,11 @@ struct TiledLaunch {
 };
 
 template <int EPI>
-static int launch_tiled_t(const ExactArgs &a, const TiledLaunch &t, int planes, cudaStream_t s)
+static int launch_tiled_t(const ExactArgs &a, const TiledLaunch &t, int planes, int device, cudaStream_t s)
 {
-	static bool attr_set = false;                  // opt in to > 48 KB of dynamic shared memory once
-	if (!attr_set) {
-		cudaFuncSetAttribute(k_tiled_minmax<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-		attr_set = true;
-	}
+	int rc;
 	if (t.line) {
-		static bool line_attr_set = false;
-		if (!line_attr_set) {
-			cudaFuncSetAttribute(k_line_minmax<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-			line_attr_set = true;
-		}
+		if ((rc = morsi_optin_smem((const void *)k_line_minmax<EPI>, device, 200 * 1024))) return rc;
 		const LineGeom &g = *t.line;
 		const int per_y = g.vertical ? g.nb * g.L : g.nl;     // output rows per CTA
 		const int per_x = g.vertical ? g.nl : g.nb * g.L;
@@ -111,6 +121,7 @@ static int launch_tiled_t(const ExactArgs &a, const TiledLaunch &t, int planes, 
 		MORSI_CU(cudaGetLastError());
 		return MORSI_OK;
 	}
+	if ((rc = morsi_optin_smem((const void *)k_tiled_minmax<EPI>, device, 200 * 1024))) return rc;
 	const int rows_y = (a.y_rows + TILED_TY - 1) / TILED_TY;
 	for (int r0 = 0; r0 < rows_y; r0 += 65535) {   // gridDim.y limit
 		ExactArgs sub = a;
@@ -127,10 +138,10 @@ static int launch_tiled_t(const ExactArgs &a, const TiledLaunch &t, int planes, 
 	return MORSI_OK;
 }
 
-static int launch_tiled(int epi, const ExactArgs &a, const TiledLaunch &t, int planes, cudaStream_t s)
+static int launch_tiled(int epi, const ExactArgs &a, const TiledLaunch &t, int planes, int device, cudaStream_t s)
 {
 	switch (epi) {
-#define C(E) case E: return launch_tiled_t<E>(a, t, planes, s);
+#define C(E) case E: return launch_tiled_t<E>(a, t, planes, device, s);
 	C(EPI_A) C(EPI_B) C(EPI_B_SUB_A) C(EPI_X_SUB_A) C(EPI_B_SUB_X) C(EPI_LAP) C(EPI_ENH)
 	C(EPI_BLUR) C(EPI_A_SUB_B) C(EPI_X_SUB_B) C(EPI_A_SUB_X) C(EPI_IBLUR) C(EPI_EBLUR)
 	C(EPI_CBLUR) C(EPI_AB)
@@ -208,7 +219,7 @@ static int run_minmax_passes(MorsiCtx *c, const DevElement *de, const MorsiJob &
 			tmin = Band{(float *)p0, t0, tps}; tmax = Band{(float *)p1, t0, tps}; }
 		else if (plan.t_min) { s1.y = (float *)p0; epi1 = EPI_A; tmin = Band{(float *)p0, t0, tps}; }
 		else { s1.y = (float *)p0; epi1 = EPI_B; tmax = Band{(float *)p0, t0, tps}; }
-		if (tl) { TiledLaunch t1 = *tl; t1.g.two_tiles = 0; rc = launch_tiled(epi1, s1, t1, job.planes, job.stream); }
+		if (tl) { TiledLaunch t1 = *tl; t1.g.two_tiles = 0; rc = launch_tiled(epi1, s1, t1, job.planes, c->device, job.stream); }
 		else rc = launch_exact(epi1, s1, job.planes, job.stream);
 		if (rc) return rc;
 	}
@@ -220,7 +231,7 @@ static int run_minmax_passes(MorsiCtx *c, const DevElement *de, const MorsiJob &
 		t2.g.two_tiles = !tl->line && plan.a_from && plan.b_from && a.a_src.p != a.b_src.p;
 		if (t2.g.two_tiles) t2.smem += (size_t)t2.g.pw * t2.g.ph * sizeof(float);
 		if (t2.smem > 200 * 1024) return morsi_set_error(MORSI_ERR_INVALID, "tiled: element too large for two tiles");
-		return launch_tiled(plan.epi, a, t2, job.planes, job.stream);
+		return launch_tiled(plan.epi, a, t2, job.planes, c->device, job.stream);
 	}
 	return launch_exact(plan.epi, a, job.planes, job.stream);
 }
@@ -324,8 +335,8 @@ int morsi_run_tiled(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int 
 	if (worst > 200 * 1024) return MORSI_OK;
 	if (plan.special == 2) {
 		// rank: one pass, no temporaries, exact in any order (no gated re-run needed)
-		static bool attr_set = false;
-		if (!attr_set) { cudaFuncSetAttribute(k_tiled_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+		int rc = morsi_optin_smem((const void *)k_tiled_rank, c->device, 200 * 1024);
+		if (rc) return rc;
 		const int rows_y = (job.y_rows + TILED_TY - 1) / TILED_TY;
 		for (int r0 = 0; r0 < rows_y; r0 += 65535) {
 			const int nb = rows_y - r0 < 65535 ? rows_y - r0 : 65535;
@@ -364,16 +375,14 @@ int morsi_dispatch(MorsiCtx *c, const int *e, const MorsiJob &job)
 		rc = morsi_run_small(c, de, job, flag, &handled);   // clears the flag itself when its kernel uses it
 		if (rc) return rc;
 		if (!handled) MORSI_CU(cudaMemsetAsync(flag, 0, sizeof(int), job.stream));
-		static const bool old_march = getenv("MORSI_DISK") && !strcmp(getenv("MORSI_DISK"), "0");
-		if (!handled && !old_march) { rc = morsi_run_disk(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 2; }
-		if (!handled) { rc = morsi_run_march(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 3; }
+		if (!handled) { rc = morsi_run_disk(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 2; }
 		if (!handled) { rc = morsi_run_median3(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 4; }
 		if (!handled) { rc = morsi_run_median(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 4; }
 		if (!handled) { rc = morsi_run_line(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 7; }
 		if (!handled) { rc = morsi_run_tiled(c, de, job, flag, &handled); if (rc) return rc; if (handled == 1) handled = 5; }
 		if (getenv("MORSI_CUDA_TRACE"))
 			fprintf(stderr, "morsi_cuda: op %d n=%d %dx%dx%d rows [%d,+%d): %s\n", job.op, de->n, job.w, job.h, job.planes,
-				job.y_row0, job.y_rows, handled == 1 ? "small" : handled == 2 ? "disk" : handled == 3 ? "march (old)" :
+				job.y_row0, job.y_rows, handled == 1 ? "small" : handled == 2 ? "disk" :
 				handled == 4 ? "median" : handled == 5 ? "tiled" : handled == 6 ? "complete in one pass (3x3 with in-kernel signed zeros / tiled rank)" : handled == 7 ? "line (van Herk)" : "exact only");
 		if (handled == 6) return MORSI_OK;             // exact as it stands: tiled rank, 3x3 with in-kernel signed zeros
 		if (handled)

@@ -3,13 +3,14 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <map>
+#include <mutex>
 #include <string>
 
 #include "../../include/morsi_cuda.h"
 #include "common.cuh"
 #include "element.h"
 
-#define MORSI_WS_SLOTS 8   // 0-3: kernel temporaries, 4-5: host-pipeline staging, 6-7: pitched copies (k_disk)
+#define MORSI_WS_SLOTS 10  // 0-3: kernel temporaries, 4-5: host-pipeline staging, 6-7: pitched copies (k_disk), 8-9: morsi_all results
 #define MORSI_LANES 4   // lane 0: the *_device entry points; 1..3: host-pointer pipeline
 
 // compiled form of a row-run element (k_rowrun.cu)
@@ -39,6 +40,11 @@ struct MorsiCtx {
 	void *ws[MORSI_LANES][MORSI_WS_SLOTS] = {};
 	size_t ws_bytes[MORSI_LANES][MORSI_WS_SLOTS] = {};
 	std::map<std::string, DevElement> elements;
+	// mu guards `elements` and the workspace table; host_mu serialises the
+	// host-pointer entry points on this device (they own lanes 1..3), so two
+	// host threads may call into one device.  The *_device entry points share
+	// lane 0's temporaries: one stream at a time per device (documented).
+	std::mutex mu, host_mu;
 };
 
 // one dispatch: `planes` planes, each a band of a w x h plane
@@ -72,10 +78,10 @@ int morsi_ws_get(MorsiCtx *c, int lane, int slot, size_t bytes, void **out);
 int morsi_element_get(MorsiCtx *c, const int *e, const DevElement **out);
 void morsi_element_compile(MorsiCtx *c, DevElement *d);
 int morsi_dispatch(MorsiCtx *c, const int *e, const MorsiJob &job);
+int morsi_optin_smem(const void *kernel, int device, int bytes);
 // fast kernel families: set *handled = 1 when they took the job
 int morsi_run_small(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_disk(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
-int morsi_run_march(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_median(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_median3(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_tiled(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);

@@ -131,8 +131,21 @@ int morsi_element_analyze(const int *e, morsi_element_info *info)
 
 	/* occupancy grid over the box, only when it is small enough to matter */
 	long bw = (long)xmax - xmin + 1, bh = (long)ymax - ymin + 1;
-	if (bw > 2 * MORSI_MAX_REACH_ROWRUN + 1 || bh > 2 * MORSI_MAX_REACH_ROWRUN + 1)
+	if (bw > 2 * MORSI_MAX_REACH_ROWRUN + 1 || bh > 2 * MORSI_MAX_REACH_ROWRUN + 1) {
+		/* long one-row / one-column lists (hrecR, vrecR, user lines): the line
+		 * kernels need to know whether the list is a run without repeats */
+		if ((bw == 1 || bh == 1) && bw * bh <= (1L << 24)) {
+			unsigned char *seen = calloc((size_t)(bw * bh), 1);
+			if (!seen) { info->has_duplicates = 1; return 0; }
+			for (int k = 0; k < n; k++) {
+				long t = bw == 1 ? (e[5 + 2*k] - e[3]) - ymin : (e[4 + 2*k] - e[2]) - xmin;
+				if (seen[t]) info->has_duplicates = 1;
+				seen[t] = 1;
+			}
+			free(seen);
+		}
 		return 0;
+	}
 	unsigned char *grid = calloc((size_t)(bw * bh), 1);
 	if (!grid) return 0;
 	for (int k = 0; k < n; k++) {

@@ -10,6 +10,7 @@
 // needed on this entry point.
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -23,6 +24,7 @@ static int run_chunks(int device, int op, const int *e, const float *x, float *y
 	MorsiCtx *c;
 	int rc = morsi_ctx_get(device, &c);
 	if (rc) return rc;
+	std::lock_guard<std::mutex> host_lk(c->host_mu);
 	size_t max_in = 0, max_out = 0;
 	for (const Chunk &k : chunks) {
 		int i0 = std::max(0, k.r0 - up), i1 = std::min(h, k.r1 + down);
@@ -136,11 +138,13 @@ extern "C" int morsi_cuda_apply_all(const int *e, const float *x, float *const o
 	MorsiCtx *c;
 	int rc = morsi_ctx_current(&c);
 	if (rc) return rc;
+	std::lock_guard<std::mutex> host_lk(c->host_mu);
 	const size_t bytes = (size_t)w * h * planes * sizeof(float);
 	void *d_x, *d_y[2];
 	if ((rc = morsi_ws_get(c, 1, 4, bytes, &d_x))) return rc;
-	if ((rc = morsi_ws_get(c, 2, 4, bytes, &d_y[0]))) return rc;
-	if ((rc = morsi_ws_get(c, 3, 4, bytes, &d_y[1]))) return rc;
+	// all three on lane 1: stream-ordered allocations belong to the stream that runs the kernels
+	if ((rc = morsi_ws_get(c, 1, 8, bytes, &d_y[0]))) return rc;
+	if ((rc = morsi_ws_get(c, 1, 9, bytes, &d_y[1]))) return rc;
 	cudaStream_t s_run = c->lane_stream[1], s_copy = c->lane_stream[2];
 	cudaEvent_t done[2], freed[2];
 	for (int i = 0; i < 2; i++) {

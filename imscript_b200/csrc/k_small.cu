@@ -601,6 +601,8 @@ int morsi_run_small(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int 
 	while (rpw > min_rpw && (long long)gx * ((job.y_rows + rpw * segs - 1) / (rpw * segs)) * job.planes < 4LL * c->sm_count)
 		rpw /= 2;
 	if (forced_rpw > 0) rpw = forced_rpw;
+	// gridDim.y <= 65535: very tall bands march longer per warp
+	while ((job.y_rows + rpw * segs - 1) / (rpw * segs) > 65535) rpw *= 2;
 	a.rows_per_warp = rpw;
 	dim3 block(32, 8);
 	dim3 grid(gx, (job.y_rows + rpw * segs - 1) / (rpw * segs), job.planes);

@@ -109,6 +109,15 @@ static int ctx_create(int device, MorsiCtx **out)
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	for (int l = 0; l < MORSI_LANES; l++)
 		CU(cudaStreamCreateWithFlags(&c->lane_stream[l], cudaStreamNonBlocking));
+	{
+		// keep stream-ordered workspace memory cached in the pool between calls
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+			unsigned long long keep = ~0ull;
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		}
+		cudaGetLastError();
+	}
 	CU(cudaMalloc(&c->d_flag, 64));
 	CU(cudaMemset(c->d_flag, 0, 64));
 	CU(cudaMallocHost(&c->h_flag, 64));
@@ -160,7 +169,9 @@ extern "C" void morsi_cuda_shutdown(void)
 		cudaStreamSynchronize(c->stream);
 		for (auto &e : c->elements) { cudaFree(e.second.d_offs); cudaFree(e.second.d_tile_offs); }
 		for (int l = 0; l < MORSI_LANES; l++)
-			for (int i = 0; i < MORSI_WS_SLOTS; i++) cudaFree(c->ws[l][i]);
+			for (int i = 0; i < MORSI_WS_SLOTS; i++)
+				if (c->ws[l][i]) { if (l > 0) cudaFreeAsync(c->ws[l][i], c->lane_stream[l]); else cudaFree(c->ws[l][i]); }
+		for (int l = 0; l < MORSI_LANES; l++) if (c->lane_stream[l]) cudaStreamSynchronize(c->lane_stream[l]);
 		for (int l = 0; l < MORSI_LANES; l++) if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
 		cudaFree(c->d_flag);
 		cudaFreeHost(c->h_flag);
@@ -171,15 +182,23 @@ extern "C" void morsi_cuda_shutdown(void)
 	g_current = -1;
 }
 
+// Workspace slots grow on demand.  Lanes 1..3 belong to the library's own
+// streams: their slots are stream-ordered allocations (cudaMallocAsync /
+// cudaFreeAsync on the lane's stream), so growing one never stalls the other
+// lanes.  Lane 0 serves caller-supplied streams: a growth there waits for the
+// device (rare: sizes only ever grow).
 int morsi_ws_get(MorsiCtx *c, int lane, int slot, size_t bytes, void **out)
 {
+	std::lock_guard<std::mutex> lk(c->mu);
 	if (c->ws_bytes[lane][slot] < bytes) {
+		const bool async = lane > 0;
 		if (c->ws[lane][slot]) {
-			CU(cudaDeviceSynchronize());
-			CU(cudaFree(c->ws[lane][slot]));
+			if (async) CU(cudaFreeAsync(c->ws[lane][slot], c->lane_stream[lane]));
+			else { CU(cudaDeviceSynchronize()); CU(cudaFree(c->ws[lane][slot])); }
 			c->ws[lane][slot] = nullptr; c->ws_bytes[lane][slot] = 0;
 		}
-		CU(cudaMalloc(&c->ws[lane][slot], bytes));
+		if (async) CU(cudaMallocAsync(&c->ws[lane][slot], bytes, c->lane_stream[lane]));
+		else CU(cudaMalloc(&c->ws[lane][slot], bytes));
 		c->ws_bytes[lane][slot] = bytes;
 	}
 	*out = c->ws[lane][slot];
@@ -190,6 +209,7 @@ int morsi_ws_get(MorsiCtx *c, int lane, int slot, size_t bytes, void **out)
 int morsi_element_get(MorsiCtx *c, const int *e, const DevElement **out)
 {
 	if (!e || e[0] < 0) return morsi_set_error(MORSI_ERR_INVALID, "bad structuring element");
+	std::lock_guard<std::mutex> lk(c->mu);
 	std::string key((const char *)e, (size_t)(4 + 2 * (size_t)e[0]) * sizeof(int));
 	auto it = c->elements.find(key);
 	if (it != c->elements.end()) { *out = &it->second; return MORSI_OK; }
@@ -283,6 +303,19 @@ extern "C" int morsi_cuda_sync(void *stream)
 {
 	MorsiCtx *c; int rc = morsi_ctx_current(&c); if (rc) return rc;
 	CU(cudaStreamSynchronize(pick_stream(c, stream)));
+	return MORSI_OK;
+}
+extern "C" int morsi_cuda_stream_create(void **stream)
+{
+	MorsiCtx *c; int rc = morsi_ctx_current(&c); if (rc) return rc;
+	cudaStream_t s;
+	CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+	*stream = (void *)s;
+	return MORSI_OK;
+}
+extern "C" int morsi_cuda_stream_destroy(void *stream)
+{
+	CU(cudaStreamDestroy((cudaStream_t)stream));
 	return MORSI_OK;
 }
 extern "C" int morsi_cuda_event_create(void **ev)

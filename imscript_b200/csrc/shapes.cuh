@@ -1,5 +1,5 @@
 // shapes.cuh -- compile-time row-run structuring elements shared by the
-// march (k_march.cu) and median (k_median.cu) kernels.  A shape is its reach R
+// disk (k_disk.cu) and median (k_median.cu) kernels.  A shape is its reach R
 // and the half-width hw(dy+R) of the centred run on each row; the dispatcher
 // matches the run-length form of the caller's element list against this table.
 #pragma once

@@ -1,18 +1,21 @@
-"""Row-band sharding of one large plane across ranks (BASELINE config C4).
+"""Row-band sharding of one large plane across ranks (BASELINE config C4): the
+Python face of the morsi_shard_* C API (imscript_b200/csrc/shard.cu).
 
 One process per GPU.  Rank g owns output rows [g*h/N, (g+1)*h/N) of the plane
-and keeps them resident together with `up`/`down` halo rows.  Every step the
-halo rows are refreshed from the vertical neighbours with point-to-point
-sends (torch.distributed: NCCL over NVLink on the GPU box, gloo in the CPU
-tests) -- the only exchange the path has, no reduction, no gather -- and the
-band then goes through morsi_cuda_apply_band_device().  Bands at the image
-edge get no neighbour data: rows outside the image are absent
-(src/morsi.c:30-35).  The fused two-stage kernels recompute the intermediate
-halo locally, so the halo is stages x reach input rows (option i).
+and keeps them resident together with the halo rows of its vertical neighbours.
+The DATA PATH is entirely inside libmorsi_cuda: every step the rank's boundary
+rows are stored straight into the neighbours' halo rows over NVLink (CUDA IPC
+mappings, device-side flags), the interior rows are computed meanwhile and the
+edge strips once the halo has landed.  What Python does is plumbing: gather the
+128-byte shard handles of all ranks once (torch.distributed all_gather_object,
+MPI, a file ... anything) and call the C entry points.
 
-torch is plumbing here (device memory for the NCCL buffers, the process
-group); the kernels are libmorsi_cuda's and run on torch's current stream so
-that they are ordered with the transfers.
+`BandPlan` restates the C bookkeeping (which rows a rank owns, holds, sends and
+receives) for the CPU tests (tests/test_shard_gloo.py), where the same exchange
+is played over gloo.  Bands at the image edge get no neighbour data: rows
+outside the image are absent (src/morsi.c:30-35).  The fused two-stage kernels
+recompute the intermediate halo locally, so the halo is stages x reach input
+rows (option i).
 """
 import ctypes
 
@@ -20,7 +23,8 @@ from . import binding as B
 
 
 class BandPlan:
-    """Pure bookkeeping: which rows a rank owns, holds, sends and receives."""
+    """Pure bookkeeping: which rows a rank owns, holds, sends and receives
+    (the same arithmetic as morsi_shard_create / shard_push in shard.cu)."""
 
     def __init__(self, h, rank, world, up, down):
         self.h, self.rank, self.world, self.up, self.down = h, rank, world, up, down
@@ -33,7 +37,7 @@ class BandPlan:
         self.own_offset = self.b0 - self.i0      # held-row index of the first owned row
 
     def transfers(self):
-        """[(kind, peer, first_held_row, n_rows)]: what exchange() posts, in order.
+        """[(kind, peer, first_held_row, n_rows)]: what an exchange moves, in order.
         The band of a neighbour may be shorter than the halo (many ranks, small
         images): only the rows the neighbour actually owns are exchanged here."""
         t = []
@@ -59,7 +63,8 @@ class BandPlan:
 
 
 def exchange(x, plan, dist):
-    """Refresh the halo rows of the held band `x` (a (rows_held, w) tensor)."""
+    """The halo exchange over torch.distributed point-to-point calls, for the CPU
+    (gloo) tests of the bookkeeping; the GPU path does this inside libmorsi_cuda."""
     if plan.world == 1:
         return
     ops = []
@@ -70,43 +75,64 @@ def exchange(x, plan, dist):
         req.wait()
 
 
-class BandJob:
-    def __init__(self, L, op, e, w, h, rank, world, dist, torch, seed, dist_kind=0):
-        self.L, self.op, self.w, self.h = L, op, w, h
-        self.dist, self.torch = dist, torch
+def gather_handles(handle, dist=None, world=1):
+    """All ranks' shard handles, in rank order, as one bytes object (plumbing:
+    any transport will do; here torch.distributed's object all-gather)."""
+    handle = bytes(handle)
+    assert len(handle) == B.SHARD_HANDLE_BYTES
+    if dist is None or world == 1:
+        return handle
+    out = [None] * world
+    dist.all_gather_object(out, handle)
+    assert all(isinstance(o, bytes) and len(o) == B.SHARD_HANDLE_BYTES for o in out)
+    return b"".join(out)
+
+
+class ShardJob:
+    """One rank of a row-band-sharded plane, driven through the C API.
+    Buffers 0 and 1 are alternating inputs (a stream of images is uploaded into
+    one while the other is processed), buffer 2 receives the result."""
+
+    def __init__(self, L, op, e, w, h, rank, world, device, dist=None, seed=4, dist_kind=0, nbuf=3):
+        self.L, self.op, self.w, self.h, self.rank, self.world = L, op, w, h, rank, world
         self.e = e
         self.e_p = e.ctypes.data_as(B._i32p)
         up, down = B.halo_rows(op, e)
-        self.plan = p = BandPlan(h, rank, world, up, down)
-        if not p.halo_complete():
-            raise B.MorsiError(1, f"bands of {h // world} rows are shorter than the {up}-row halo")
-        if torch is not None:
-            self.x = torch.empty((p.rows_held, w), dtype=torch.float32, device="cuda")
-            self.y = torch.empty((p.rows_own, w), dtype=torch.float32, device="cuda")
-            self.x_ptr, self.y_ptr = self.x.data_ptr(), self.y.data_ptr()
-            self.stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        else:
-            self._bx = B.DeviceBuffer(p.rows_held * w * 4)
-            self._by = B.DeviceBuffer(p.rows_own * w * 4)
-            self.x_ptr, self.y_ptr = self._bx.ptr, self._by.ptr
-            self.stream = None
-        # own rows only: the halo rows arrive through the exchange
-        own = self.x_ptr + p.own_offset * w * 4
-        B.check(L.morsi_cuda_synth(own, w, p.rows_own, p.b0, 0, seed, dist_kind, self.stream))
-        B.check(L.morsi_cuda_sync(self.stream))
-
-    def exchange(self):
-        if self.plan.world > 1:
-            exchange(self.x, self.plan, self.dist)
-
-    def compute(self):
+        self.plan = BandPlan(h, rank, world, up, down)
+        self.s = B._vp()
+        B.check(L.morsi_shard_create(ctypes.byref(self.s), device, rank, world, w, h, max(up, down), nbuf))
+        hd = ctypes.create_string_buffer(B.SHARD_HANDLE_BYTES)
+        B.check(L.morsi_shard_handle(self.s, hd))
+        table = gather_handles(hd.raw, dist, world)
+        B.check(L.morsi_shard_connect(self.s, table))
+        self.stream = B._vp(L.morsi_shard_stream(self.s))
+        self.k = 0
         p = self.plan
-        B.check(self.L.morsi_cuda_apply_band_device(self.op, self.e_p, self.x_ptr, p.i0, p.rows_held,
-                                                    self.y_ptr, p.b0, p.rows_own, self.w, self.h, self.stream))
+        self.n_inputs = 2 if nbuf >= 3 else 1
+        self.out_buf = nbuf - 1
+        # own rows only: the halo rows arrive through the exchange
+        for b in range(self.n_inputs):
+            B.check(L.morsi_cuda_synth(self.buffer_ptr(b) + p.own_offset * w * 4, w, p.rows_own, p.b0, 0, seed,
+                                       dist_kind, self.stream))
+        B.check(L.morsi_shard_sync(self.s))
+        self.h_x = self.h_y = None
+
+    def buffer_ptr(self, b):
+        return self.L.morsi_shard_buffer(self.s, b)
+
+    def out_ptr(self):
+        """device pointer of the first OWNED output row"""
+        return self.buffer_ptr(self.out_buf) + self.plan.own_offset * self.w * 4
 
     def step(self):
-        self.exchange()
-        self.compute()
+        B.check(self.L.morsi_shard_apply(self.s, self.op, self.e_p, self.k % self.n_inputs, self.out_buf))
+        self.k += 1
+
+    def sync(self):
+        B.check(self.L.morsi_shard_sync(self.s))
+
+    def halo_bytes(self):
+        return int(self.L.morsi_shard_halo_bytes(self.s))
 
     # ---- end to end: the band lives in (pinned) HOST memory -----------------
     def host_buffers(self):
@@ -116,23 +142,23 @@ class BandJob:
         nbytes = p.rows_own * self.w * 4
         B.check(L.morsi_cuda_host_alloc(ctypes.byref(self.h_x), nbytes))
         B.check(L.morsi_cuda_host_alloc(ctypes.byref(self.h_y), nbytes))
-        own = self.x_ptr + p.own_offset * self.w * 4
-        B.check(L.morsi_cuda_memcpy_d2h(self.h_x, own, nbytes, self.stream))
-        B.check(L.morsi_cuda_sync(self.stream))
+        B.check(L.morsi_cuda_memcpy_d2h(self.h_x, self.buffer_ptr(0) + p.own_offset * self.w * 4, nbytes, self.stream))
+        self.sync()
         return nbytes
 
     def e2e_step(self):
-        """host -> device copy of the owned rows, halo exchange between the
-        ranks, the kernels, device -> host copy of the result, all on one stream"""
-        p, L = self.plan, self.L
-        nbytes = p.rows_own * self.w * 4
-        own = self.x_ptr + p.own_offset * self.w * 4
-        B.check(L.morsi_cuda_memcpy_h2d(own, self.h_x, nbytes, self.stream))
-        self.exchange()
-        self.compute()
-        B.check(L.morsi_cuda_memcpy_d2h(self.h_y, self.y_ptr, nbytes, self.stream))
-        B.check(L.morsi_cuda_sync(self.stream))
+        """morsi_shard_apply_host: boundary rows up and pushed first, then the band
+        streams through upload / kernels / download; synchronous"""
+        B.check(self.L.morsi_shard_apply_host(self.s, self.op, self.e_p, self.h_x, self.h_y))
 
     def free_host_buffers(self):
-        self.L.morsi_cuda_host_free(self.h_x)
-        self.L.morsi_cuda_host_free(self.h_y)
+        if self.h_x is not None:
+            self.L.morsi_cuda_host_free(self.h_x)
+            self.L.morsi_cuda_host_free(self.h_y)
+            self.h_x = self.h_y = None
+
+    def destroy(self):
+        self.free_host_buffers()
+        if self.s:
+            self.L.morsi_shard_destroy(self.s)
+            self.s = None

@@ -102,7 +102,11 @@ void morsi_cuda_shutdown(void);
  * operation(y+k*w*h, x+k*w*h, w, h, e): HOST pointers in, HOST pointers out,
  * synchronous.  Copies to the device(s), runs the sm_100a kernels, copies back.
  * When MORSI_CUDA_DEVICES=N (N>1) is set, planes (or, for a single plane, row
- * bands with halo rows exchanged over peer copies) are spread over N devices. */
+ * bands) are spread over N devices; on this entry point every device takes the
+ * halo rows of its bands from the caller's host buffer together with the band,
+ * so no device-to-device traffic is needed.  Device-resident sharding with a
+ * halo exchange over NVLink is morsi_shard_* / morsi_cuda_apply_sharded below.
+ * Thread safety: host-pointer calls on one device are serialised internally. */
 int morsi_cuda_apply(int op, const int *e, const float *x, float *y,
 		int w, int h, int planes);
 
@@ -132,6 +136,56 @@ int morsi_cuda_apply_band_device(int op, const int *e,
 /* Input rows needed above (*up) and below (*down) an output band. */
 int morsi_cuda_halo_rows(int op, const int *e, int *up, int *down);
 
+/* ---- row-band sharding of one plane across devices ---------
+ * The reference is one thread in one process; this is how an image too large
+ * (or too slow) for one GPU, or an iterated operation on it, runs on the GPUs
+ * of a box.  Rank g of nranks owns rows [g*h/nranks, (g+1)*h/nranks) and holds
+ * them plus `halo_rows` rows of each vertical neighbour in `nbuf` (2..4)
+ * device buffers of equal shape.  A step pushes the rank's boundary rows
+ * straight into the neighbours' halo rows (peer stores over NVLink, CUDA IPC
+ * between processes / peer access inside one; device-side flag words order the
+ * ranks, no host synchronisation, no collective) and runs the kernels of
+ * morsi_cuda_apply_band_device: the interior rows overlap the transfer, the
+ * edge strips follow it.  Ranks are processes with one device each or devices
+ * of one process; all ranks must issue the same sequence of apply calls.
+ * Image-edge bands get no neighbour data (src/morsi.c:30-35); the halo an
+ * operation needs is stages x reach rows (src/morsi.c:65, morsi_cuda_halo_rows).
+ * Failures of the exchange (unreachable peer, a neighbour that never arrives
+ * within MORSI_SHARD_TIMEOUT_MS) return MORSI_ERR_COMM. */
+typedef struct morsi_shard morsi_shard;
+#define MORSI_SHARD_HANDLE_BYTES 128
+int morsi_shard_create(morsi_shard **s, int device, int rank, int nranks,
+		int w, int h, int halo_rows, int nbuf);
+/* A rank's handle (MORSI_SHARD_HANDLE_BYTES bytes, position independent): the
+ * caller gathers the handles of all ranks -- any transport: MPI, a file,
+ * torch.distributed -- and passes the nranks x 128-byte table to connect(). */
+int morsi_shard_handle(const morsi_shard *s, void *handle);
+int morsi_shard_connect(morsi_shard *s, const void *handles);
+int morsi_shard_rows(const morsi_shard *s, int *own_row0, int *own_rows,
+		int *held_row0, int *held_rows);
+/* Device pointer of the first HELD row of buffer `buf` (row pitch w). */
+float *morsi_shard_buffer(morsi_shard *s, int buf);
+/* The rank's stream (a cudaStream_t): fill buffers and record events on it. */
+void *morsi_shard_stream(morsi_shard *s);
+/* dst's owned rows = op(src) : halo exchange + kernels, asynchronous. */
+int morsi_shard_apply(morsi_shard *s, int op, const int *e, int src_buf, int dst_buf);
+/* Host rows in, host rows out (this rank's OWNED rows, pitch w; pinned memory
+ * overlaps): boundary rows first and pushed at once, then the band streams
+ * through in chunks on upload / kernel / download streams.  Synchronous. */
+int morsi_shard_apply_host(morsi_shard *s, int op, const int *e, const float *x_own, float *y_own);
+/* The exchange of a step on its own: refresh the halo rows of `buf` (up rows
+ * above, down rows below) from the neighbours; asynchronous. */
+int morsi_shard_exchange(morsi_shard *s, int buf, int up, int down);
+/* Wait for the rank's streams; MORSI_ERR_COMM if an exchange timed out. */
+int morsi_shard_sync(morsi_shard *s);
+long long morsi_shard_halo_bytes(const morsi_shard *s);   /* pushed by the last apply */
+int morsi_shard_destroy(morsi_shard *s);
+/* One process, ndev devices: host plane in, host plane out, the operation
+ * applied `iterations` times with the bands resident between iterations and
+ * only halo rows travelling device to device. */
+int morsi_cuda_apply_sharded(int op, const int *e, const float *x, float *y,
+		int w, int h, int ndev, int iterations);
+
 /* Force a kernel family: 0 = automatic, 1 = order-preserving exact kernels
  * only (the signed-zero-safe path), 2 = fast kernels without the signed-zero
  * re-run (benchmark use).  Also settable with MORSI_CUDA_PATH=auto|exact|fast. */
@@ -152,6 +206,8 @@ int morsi_cuda_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes, void *st
 int morsi_cuda_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes, void *stream);
 int morsi_cuda_memcpy_d2d(void *d_dst, const void *d_src, size_t bytes, void *stream);
 int morsi_cuda_sync(void *stream);
+int morsi_cuda_stream_create(void **stream);
+int morsi_cuda_stream_destroy(void *stream);
 /* Device-side synthetic image of SURVEY.md 8(d): distribution 0 = uniform
  * [0,1) on a 2^-24 grid, 1 = integers 0..255, 2 = distribution 0 with NaN /
  * +-Inf / +-0 sprinkled in; value = f(seed, plane, row, column), so bands and

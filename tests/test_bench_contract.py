@@ -33,3 +33,23 @@ def test_ours_refuses_without_a_gpu():
                          text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0
     assert "no CUDA device" in (out.stderr + out.stdout)
+
+
+def test_reference_arm_never_maps_the_cuda_library():
+    """the reference arm is the reference's CPU code alone: libmorsi_cuda.so must not be loaded by it"""
+    code = ("import sys; sys.path.insert(0, %r); import bench; "
+            "bench.run_reference_once('c1', 1); "
+            "print('MAPPED' if 'libmorsi_cuda' in open('/proc/self/maps').read() else 'CLEAN')" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip().endswith("CLEAN")
+
+
+def test_numpy_synth_equals_the_library_synth():
+    import numpy as np
+    import bench
+    import imscript_b200 as M
+    for (w, rows, row0, plane, seed) in [(1024, 768, 1664, 3, 2), (37, 5, 0, 0, 1), (40000, 3, 39990, 0, 4)]:
+        a = bench.synth_numpy(w, rows, row0, plane, seed)
+        b = M.synth_host(w, rows, row0=row0, plane=plane, seed=seed)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
