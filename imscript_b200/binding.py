@@ -42,6 +42,9 @@ class MorsiError(RuntimeError):
 
 
 def lib_path(name="libmorsi_cuda.so"):
+    # MORSI_CUDA_LIB: an alternative build of the library (A/B measurements of kernel variants)
+    if name == "libmorsi_cuda.so" and os.environ.get("MORSI_CUDA_LIB"):
+        return os.environ["MORSI_CUDA_LIB"]
     return os.path.join(HERE, "lib", name)
 
 

@@ -41,6 +41,8 @@
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <type_traits>
 
 #include <cuda.h>
 
@@ -60,6 +62,7 @@ struct DiskArgs {
 	int band_rows;     // output rows per CTA
 	int epi;
 	int *flag;
+	int both = 0;      // 1: erosion and dilation in one pass (k_disk_both), epilogue epi(a, b, x)
 };
 
 // ---- small PTX wrappers ------------------------------------------------------------
@@ -76,15 +79,30 @@ __device__ __forceinline__ void mbar_arrive_tx(unsigned bar, unsigned bytes)
 {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+// try_wait suspends the thread for a hardware time slice; the loop is left when
+// the phase completes.  A wait that lasts seconds is a protocol bug (a legal one
+// lasts microseconds): trap, so that it surfaces as a launch failure instead of
+// a hung device.
+__device__ __forceinline__ unsigned mbar_try(unsigned bar, unsigned parity)
 {
+	unsigned ok;
 	asm volatile(
 		"{\n"
 		".reg .pred p;\n"
-		"WAIT_%=:\n"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-		"@!p bra WAIT_%=;\n"
-		"}\n" :: "r"(bar), "r"(parity) : "memory");
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+		"selp.u32 %0, 1, 0, p;\n"
+		"}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+	return ok;
+}
+static __device__ __noinline__ void mbar_wait_slow(unsigned bar, unsigned parity)
+{
+	const long long t0 = clock64();
+	while (!mbar_try(bar, parity))
+		if (clock64() - t0 > 8000000000LL) __trap();
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+	if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
 }
 // Wait executed by a whole (converged) warp.  The lanes of a warp can leave the
 // try_wait loop in different iterations; nothing would reconverge them
@@ -367,6 +385,12 @@ static __device__ __noinline__ void disk_store_tmp_masked(float *q0, float *q1, 
 // HASX (TWO only): the epilogue subtracts: tophat x - opening (ISMAX = false),
 // bothat closing - x (ISMAX = true); src/morsi.c:229-245.
 // tm: the source band as a (bw, w/bw, rows, planes) tensor, box (bw, RP/bw, 2*GP, 1).
+// Which half of the warps runs which stage alternates between the CTAs an SM
+// receives (a per-SM counter): a warp's scheduler partition is its index modulo
+// 4, so with a fixed assignment every partition would only ever host one of
+// the two roles and the cheaper role's partitions would idle.
+static __device__ unsigned g_disk_sm_turn[1024];
+
 template <class S, int C, int W, bool ISMAX, bool TWO, bool HASX>
 __global__ void __launch_bounds__(DiskCfg<S, C, W, TWO>::THREADS, DiskCfg<S, C, W, TWO>::MINB)
 k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
@@ -385,9 +409,22 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
-	const bool first = TWO && tid < K::NT;            // warp-uniform role
+#ifdef DISK_SWAP
+	__shared__ int s_swap;
+	if (TWO && tid == 0) {
+		unsigned smid;
+		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+		s_swap = (int)(atomicAdd(&g_disk_sm_turn[smid & 1023], 1u) & 1u);
+	}
+	if (TWO) __syncthreads();
+	const bool swap = TWO && s_swap != 0;
+#else
+	const bool swap = false;
+#endif
+	const bool first = TWO && ((tid < K::NT) != swap);   // warp-uniform role
 	const bool reads_input = !TWO || first;
-	const int mt = TWO ? (first ? tid : tid - K::NT) : tid;
+	const int mt = tid & (K::NT - 1);                  // thread index within its stage
+	const bool producer = reads_input && mt == 0;     // issues the TMA copies
 	const int plane = blockIdx.z;
 	const int cx0 = blockIdx.x * K::OUTW;             // first output column of the strip
 	const int o_base = blockIdx.y * p.band_rows;      // first output row of the band (relative)
@@ -424,7 +461,7 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 		mbar_arrive_tx(full_in + 8 * slot, K::GROUP_BYTES);
 		tma_load_4d(ring_u32 + slot * K::GROUP_BYTES, &tm, 0, gxb, trow0 + 2 * GP * gi, plane, full_in + 8 * slot);
 	};
-	if (tid == 0) {
+	if (producer) {
 		for (int gi = 0; gi < NG - 1 && gi < ngroups; gi++) load_group(gi);
 	}
 
@@ -477,7 +514,7 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 				if (pos == 0) {
 					// a new group: keep the producer one group ahead, then wait for ours
 					const int slot = gi % NG;
-					if (tid == 0 && gi + NG - 1 < ngroups) load_group(gi + NG - 1);
+					if (producer && gi + NG - 1 < ngroups) load_group(gi + NG - 1);
 					mbar_wait_warp(my_full + 8 * slot, (gi / NG) & 1);
 					grp = my_ring + slot * GROUP;
 					grp_empty = my_empty + 8 * slot;
@@ -486,8 +523,9 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 				const float *rowA = grp + pos * PAIR;
 				// the two outputs this step completes
 				const int o0 = 2 * g - 2 * R;
-				const bool e0 = col_ok && o0 >= 0 && o0 < nout;
-				const bool e1 = col_ok && o0 + 1 >= 0 && o0 + 1 < nout;
+				// (one unsigned compare each: 0 <= o < nout)
+				const bool e0 = col_ok && (unsigned)o0 < (unsigned)nout;
+				const bool e1 = col_ok && (unsigned)(o0 + 1) < (unsigned)nout;
 				float xv0[C], xv1[C], ov0[C], ov1[C];
 				if (TWO && HASX) {
 					if (e0) load_cols<C>(xq, xv0);
@@ -528,7 +566,7 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 						float v0[C], v1[C];
 #pragma unroll
 						for (int c = 0; c < C; c++) { v0[c] = -m0[c]; v1[c] = -m1[c]; }
-						if (tcol_all && tr >= 0 && tr + 1 < h) {
+						if (tcol_all && (unsigned)tr < (unsigned)(h - 1)) {       // rows tr, tr+1 inside the image
 							store_cols<C>(q, v0);
 							store_cols<C>(q + RP, v1);
 						} else {
@@ -593,6 +631,239 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 			}
 		}
 	}
+	if (__syncthreads_or(zmin == INT_MIN) && tid == 0) atomicOr(p.flag, 1);
+}
+
+// ---- erosion AND dilation of one input in one pass ---------------------------------------
+// gradient, laplacian, enhance, blur, cblur (src/morsi.c:157-167,187-215,265-275) need the
+// erosion a and the dilation b of the SAME image at the same pixel.  Both reductions run
+// in one CTA over one TMA ring: warps of role A march the minimum, warps of role B the
+// maximum (each group of input rows is handed back once BOTH roles have read it); role A
+// leaves its rows in a small shared-memory ring, role B picks them up when the same output
+// rows complete on its side, applies the epilogue with the centre pixel x (re-read from
+// global memory, an L2 hit: the rows went through the ring R rows earlier) and stores.
+// 8 B/sample of HBM traffic instead of the 16-24 B of two passes through a temporary image.
+template <class S, int C, int W>
+struct DiskCfgBoth {
+	using K1 = DiskCfg<S, C, W, false>;
+	static constexpr int R = K1::R, LH = K1::LH, NT = K1::NT, TW = K1::TW, OUTW = K1::OUTW, RP = K1::RP;
+	static constexpr int PERIOD = K1::PERIOD, GP = K1::GP, PAIR = K1::PAIR, GROUP = K1::GROUP, NG = K1::NG;
+	static constexpr unsigned GROUP_BYTES = K1::GROUP_BYTES;
+	static constexpr int APAIR = 2 * TW;              // role A's rows: just the strip's own columns
+	static constexpr int AGROUP = GP * APAIR;
+	static constexpr int NACC = K1::NACC;
+	static constexpr int THREADS = 2 * NT;
+	static constexpr size_t SMEM = (size_t)NG * (GROUP + AGROUP) * sizeof(float) + 4 * NG * sizeof(unsigned long long) + 128;
+	static constexpr int REGS = (C * (2 * R + 2) > 64) ? 255 : (THREADS >= 256 ? DISK_REGS_SMALL_W4 : DISK_REGS_SMALL);
+	static constexpr int MINB = 65536 / (REGS * THREADS) > 0 ? 65536 / (REGS * THREADS) : 1;
+};
+
+template <class S, int C, int W>
+__global__ void __launch_bounds__(DiskCfgBoth<S, C, W>::THREADS, DiskCfgBoth<S, C, W>::MINB)
+k_disk_both(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
+{
+	using K = DiskCfgBoth<S, C, W>;
+	constexpr int R = K::R, LH = K::LH, RP = K::RP, PERIOD = K::PERIOD, GP = K::GP, NG = K::NG;
+	constexpr int PAIR = K::PAIR, GROUP = K::GROUP, APAIR = K::APAIR, AGROUP = K::AGROUP, TW = K::TW;
+	extern __shared__ unsigned char smem_raw[];
+	float *ring = reinterpret_cast<float *>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));   // NG groups of input rows
+	float *aring = ring + (size_t)NG * GROUP;                          // NG groups of role A's result rows
+	const unsigned bars = smem_u32(aring + (size_t)NG * AGROUP);
+	const unsigned full_in = bars, empty_in = bars + 8 * NG;
+	const unsigned full_a = bars + 16 * NG, empty_a = bars + 24 * NG;
+	__shared__ int s_swap;
+
+	const int tid = threadIdx.x;
+	const int lane = tid & 31;
+	if (tid == 0) {
+		for (int i = 0; i < NG; i++) {
+			mbar_init(full_in + 8 * i, 1); mbar_init(empty_in + 8 * i, 2 * W);
+			mbar_init(full_a + 8 * i, W); mbar_init(empty_a + 8 * i, W);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("prefetch.tensormap [%0];" :: "l"(&tm) : "memory");
+		unsigned smid;
+		asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+		s_swap = (int)(atomicAdd(&g_disk_sm_turn[smid & 1023], 1u) & 1u);
+	}
+	__syncthreads();
+	const bool first = (tid < K::NT) != (s_swap != 0);   // role A (minimum); warp-uniform
+	const int mt = tid & (K::NT - 1);
+	const bool producer = first && mt == 0;
+	const int plane = blockIdx.z;
+	const int cx0 = blockIdx.x * K::OUTW;
+	const int o_base = blockIdx.y * p.band_rows;
+	const int nout = min(p.band_rows, p.y_rows - o_base);
+	const int Y0 = p.y_row0 + o_base;
+	const int w = p.w;
+	const long long pitch = p.pitch;
+	const int G2 = (nout + 2 * R + 1) / 2;            // row pairs marched
+	const int NOP = (nout + 1) / 2;                   // output row pairs
+	const int in_row0 = Y0 - R;
+	const int gc0 = cx0 - LH;
+	const int gxb = (gc0 >= 0 ? gc0 : gc0 - bw + 1) / bw;
+	const int shift = gc0 - gxb * bw;
+
+	const unsigned ring_u32 = smem_u32(ring);
+	const int trow0 = in_row0 - p.src.row0;
+	const int ngroups = (G2 + GP - 1) / GP;
+	// Role B holds input groups too, and it may sit in the middle of one while it waits for
+	// rows of role A: the producer (a thread of role A) must therefore never BLOCK on a
+	// slot while role A still has rows to deliver from the groups it already holds.  It
+	// tries at every step, without waiting, and insists only at the start of the group it
+	// needs itself -- by then role A has delivered everything role B can be waiting for.
+	int next_load = 0;
+	auto issue_group = [&](int gl) {
+		const int slot = gl % NG;
+		mbar_arrive_tx(full_in + 8 * slot, K::GROUP_BYTES);
+		tma_load_4d(ring_u32 + slot * K::GROUP_BYTES, &tm, 0, gxb, trow0 + 2 * GP * gl, plane, full_in + 8 * slot);
+	};
+	if (producer) {
+		for (; next_load < NG - 1 && next_load < ngroups; next_load++) issue_group(next_load);
+	}
+
+	const float *my_ring = ring + shift + C * mt;
+	float *my_a = aring + C * mt;
+	const bool lane0 = lane == 0;
+	const int x = cx0 + C * mt;
+	const bool col_ok = !first && x < w;
+	const bool pad_edge = col_ok && x + C > w;
+	float *yq = p.y + plane * p.y_pstride + (long long)(Y0 - p.y_row0 - 2 * R) * pitch + x;
+	const float *xq = p.xop.p ? p.xop.p + plane * p.xop.pstride + (long long)(Y0 - p.xop.row0 - 2 * R) * pitch + x : nullptr;
+	const int epi = p.epi;
+	int zmin = 0;
+
+	auto run = [&](auto flavour) {
+		constexpr bool ISMAX = decltype(flavour)::value;
+		using D = DiskMarch<S, C, LH, ISMAX>;
+		float acc[C][K::NACC], hs[C][4];
+#pragma unroll
+		for (int c = 0; c < C; c++) {
+#pragma unroll
+			for (int k = 0; k < K::NACC; k++) acc[c][k] = D::init();
+#pragma unroll
+			for (int k = 0; k < 4; k++) hs[c][k] = D::init();
+		}
+		int gi = 0, agi = 0;
+		const float *grp = my_ring;
+		float *agrp = my_a;
+		unsigned grp_empty = empty_in, agrp_bar = full_a;
+#pragma unroll 1
+		for (int g0 = 0; g0 < G2; g0 += PERIOD) {
+#pragma unroll
+			for (int s = 0; s < PERIOD; s++) {
+				const int g = g0 + s;
+				if (g < G2) {
+					const int pos = s % GP;
+					if (producer) {
+						// gi - (pos != 0) = the group being consumed; group n may go into its slot once group n - NG is done
+						const int cur = pos == 0 ? gi : gi - 1;
+						if (pos == 0)
+							while (next_load <= cur && next_load < ngroups) {           // needed now: wait for the slot
+								if (next_load >= NG) mbar_wait(empty_in + 8 * (next_load % NG), ((next_load / NG) - 1) & 1);
+								issue_group(next_load++);
+							}
+						if (next_load < ngroups && next_load < cur + NG &&
+								(next_load < NG || mbar_try(empty_in + 8 * (next_load % NG), ((next_load / NG) - 1) & 1)))
+							issue_group(next_load++);
+					}
+					if (pos == 0) {
+						const int slot = gi % NG;
+						mbar_wait_warp(full_in + 8 * slot, (gi / NG) & 1);
+						grp = my_ring + slot * GROUP;
+						grp_empty = empty_in + 8 * slot;
+						gi++;
+					}
+					const float *rowA = grp + pos * PAIR;
+					const int o0 = 2 * g - 2 * R;
+					const bool e0 = col_ok && (unsigned)o0 < (unsigned)nout;
+					const bool e1 = col_ok && (unsigned)(o0 + 1) < (unsigned)nout;
+					float xv0[C], xv1[C];
+					if (ISMAX) {
+						// role B: the centre pixels of the two output rows, in flight during the reductions
+#pragma unroll
+						for (int c = 0; c < C; c++) { xv0[c] = 0.f; xv1[c] = 0.f; }
+						if (e0 && xq) load_cols<C>(xq, xv0);
+						if (e1 && xq) load_cols<C>(xq + pitch, xv1);
+					}
+					D::step(acc, hs, s % (R + 1), rowA, rowA + RP, zmin, !ISMAX,
+						[&]() { if (pos == GP - 1 && lane0) mbar_arrive(grp_empty); },
+						[&](const float (&m0)[C], const float (&m1)[C]) {
+						const int op = g - R;                                   // output row pair
+						if (op < 0) return;
+						const int apos = ((s - R) % GP + GP) % GP;
+						if (!ISMAX) {
+							// role A: rows 2 op, 2 op + 1 of the erosion -> ring
+							if (apos == 0) {
+								const int slot = agi % NG;
+								if (agi >= NG) mbar_wait_warp(empty_a + 8 * slot, ((agi / NG) - 1) & 1);
+								agrp = my_a + slot * AGROUP;
+								agrp_bar = full_a + 8 * slot;
+								agi++;
+							}
+							float *q = agrp + apos * APAIR;
+							store_cols<C>(q, m0);
+							store_cols<C>(q + TW, m1);
+							if (apos == GP - 1 || op == NOP - 1) {
+								__syncwarp();
+								if (lane0) mbar_arrive(agrp_bar);
+							}
+						} else {
+							// role B: the dilation is in m0 / m1; fetch the erosion, finish, store
+							if (apos == 0) {
+								const int slot = agi % NG;
+								mbar_wait_warp(full_a + 8 * slot, (agi / NG) & 1);
+								agrp = my_a + slot * AGROUP;
+								agrp_bar = empty_a + 8 * slot;
+								agi++;
+							}
+							const float *q = agrp + apos * APAIR;
+							float a0[C], a1[C];
+							if (C == 4) {
+								const float4 t0 = *(const float4 *)q, t1 = *(const float4 *)(q + TW);
+								a0[0] = t0.x; a0[1] = t0.y; a0[2] = t0.z; a0[3] = t0.w;
+								a1[0] = t1.x; a1[1] = t1.y; a1[2] = t1.z; a1[3] = t1.w;
+							} else {
+								const float2 t0 = *(const float2 *)q, t1 = *(const float2 *)(q + TW);
+								a0[0] = t0.x; a0[1] = t0.y; a1[0] = t1.x; a1[1] = t1.y;
+							}
+							if (e0) {
+								const float4 r = disk_epi4<true>(epi, m0[0], m0[1], C == 4 ? m0[2] : 0.f, C == 4 ? m0[3] : 0.f,
+										a0[0], a0[1], C == 4 ? a0[2] : 0.f, C == 4 ? a0[3] : 0.f,
+										xv0[0], xv0[1], C == 4 ? xv0[2] : 0.f, C == 4 ? xv0[3] : 0.f);
+								if (C == 4) *(float4 *)yq = r; else *(float2 *)yq = make_float2(r.x, r.y);
+							}
+							if (e1) {
+								const float4 r = disk_epi4<true>(epi, m1[0], m1[1], C == 4 ? m1[2] : 0.f, C == 4 ? m1[3] : 0.f,
+										a1[0], a1[1], C == 4 ? a1[2] : 0.f, C == 4 ? a1[3] : 0.f,
+										xv1[0], xv1[1], C == 4 ? xv1[2] : 0.f, C == 4 ? xv1[3] : 0.f);
+								if (C == 4) *(float4 *)(yq + pitch) = r; else *(float2 *)(yq + pitch) = make_float2(r.x, r.y);
+							}
+							// the values are in registers (the epilogue consumed them): hand the group back
+							if (apos == GP - 1 || op == NOP - 1) {
+								__syncwarp();
+								if (lane0) mbar_arrive(agrp_bar);
+							}
+							if (pad_edge) {
+#pragma unroll
+								for (int c = 0; c < C; c++)
+									if (x + c >= w) {
+										if (e0) yq[c] = CUDART_NAN_F;
+										if (e1) yq[pitch + c] = CUDART_NAN_F;
+									}
+							}
+						}
+					});
+					if (ISMAX) {
+						yq += 2 * pitch;
+						if (xq) xq += 2 * pitch;
+					}
+				}
+			}
+		}
+	};
+	if (first) run(std::false_type{});
+	else run(std::true_type{});
 	if (__syncthreads_or(zmin == INT_MIN) && tid == 0) atomicOr(p.flag, 1);
 }
 
@@ -716,6 +987,41 @@ static int disk_launch(const MorsiCtx *c, const DiskArgs &a0, int planes, int ba
 	return MORSI_OK;
 }
 
+template <class S, int C, int W>
+static int disk_both_occupancy(int device)
+{
+	using K = DiskCfgBoth<S, C, W>;
+	static int occs[64];
+	int &occ = occs[device & 63];
+	if (occ <= 0) {
+		cudaFuncSetAttribute(k_disk_both<S, C, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+		int o = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_disk_both<S, C, W>, K::THREADS, K::SMEM) != cudaSuccess || o < 1)
+			o = 1;
+		occ = o;
+	}
+	return occ;
+}
+
+template <class S, int C, int W>
+static int disk_launch_both(const MorsiCtx *c, const DiskArgs &a0, int planes, cudaStream_t st)
+{
+	using K = DiskCfgBoth<S, C, W>;
+	DiskArgs a = a0;
+	const int strips = (a.w + K::OUTW - 1) / K::OUTW;
+	const int occ = disk_both_occupancy<S, C, W>(c->device);
+	a.band_rows = pick_band_rows((long long)c->sm_count * occ, a.y_rows, (long long)strips * planes, S::R, 1, nullptr);
+	CUtensorMap tm;
+	int bw = 4;
+	int rc = disk_tensor_map(&tm, a.src, a.src_rows, a.pitch, planes, K::RP, 2 * K::GP, &bw);
+	if (rc) return rc;
+	dim3 grid(strips, (a.y_rows + a.band_rows - 1) / a.band_rows, planes);
+	k_disk_both<S, C, W><<<grid, K::THREADS, K::SMEM, st>>>(tm, a, bw);
+	morsi_count_launch(1);
+	MORSI_CU(cudaGetLastError());
+	return MORSI_OK;
+}
+
 static int disk_forced_w()
 {
 	const char *s = getenv("MORSI_DISK_W");            // 2 or 4 warps per stage; default: planned
@@ -742,6 +1048,12 @@ template <int ID, int C>
 static int disk_shape_c(MorsiCtx *c, const DiskArgs &a, int planes, bool ismax, bool two, cudaStream_t st)
 {
 	using S = Shape<ID>;
+	if (a.both) {
+		// 2 warps per role for the small disks, 4 for the ones that need every register
+		if (disk_forced_w() == 4 || (disk_forced_w() != 2 && DiskCfgBoth<S, C, 2>::REGS >= 255))
+			return disk_launch_both<S, C, 4>(c, a, planes, st);
+		return disk_launch_both<S, C, 2>(c, a, planes, st);
+	}
 	if (two && a.xop.p)
 		return ismax ? disk_run<S, C, true, true, true>(c, a, planes, st) : disk_run<S, C, false, true, true>(c, a, planes, st);
 	if (two)
@@ -886,19 +1198,34 @@ static int run_disk_passes(MorsiCtx *c, int id, const DevElement *de, const Mors
 		a.pitch = P;
 		return launch_by_id(id, c, a, job.planes, plan.t_max != 0, true, job.stream);
 	}
-	// temporaries cover the output band grown by one reach (clipped); chunk the
-	// band so that a temporary stays below 512 MiB
+	if (both1) {
+		// gradient, laplacian, enhance, blur, cblur: erosion and dilation in one pass (k_disk_both)
+		static const bool two_pass = getenv("MORSI_DISK_BOTH") && !strcmp(getenv("MORSI_DISK_BOTH"), "0");   // A/B: the round-1 two-pass form
+		// measured on B200 (profiles/r2_kdisk_both_swap_variants.txt): one pass wins for the small disks (disk7
+		// gradient 0.247 -> 0.217 ms); for the 255-register shapes the two roles, coupled through the shared
+		// input ring, lose to two passes (disk15 gradient on 40000x10000: 4.78 vs 3.68 ms)
+		if (!two_pass && 4 * (2 * R + 2) <= 64) {
+			DiskArgs a;
+			a.src = xb; a.src_rows = job.x_rows; a.other = none; a.xop = xb;
+			a.y = job.y; a.y_pstride = job.y_pstride; a.y_row0 = job.y_row0; a.y_rows = job.y_rows;
+			a.w = job.w; a.h = job.h; a.epi = plan.epi; a.flag = flag; a.band_rows = job.y_rows;
+			a.pitch = P;
+			a.both = 1;
+			return launch_by_id(id, c, a, job.planes, false, false, job.stream);
+		}
+	}
+	// one temporary of the output band's size; chunk the band so that it stays below 512 MiB
 	const long long budget = 512LL << 20;
-	long long rows_fit = budget / ((long long)P * 4 * job.planes) - 2 * R;
+	long long rows_fit = budget / ((long long)P * 4 * job.planes);
 	if (rows_fit < 8 * R + 64) rows_fit = 8 * R + 64;
 	const int chunk = (int)(rows_fit < job.y_rows ? rows_fit : job.y_rows);
 	for (int r0 = 0; r0 < job.y_rows; r0 += chunk) {
 		const int o0 = job.y_row0 + r0;
 		const int orows = job.y_rows - r0 < chunk ? job.y_rows - r0 : chunk;
 		float *ydst = job.y + (long long)r0 * P;
+		void *p0; if ((rc = morsi_ws_get(c, job.lane, 0, (size_t)P * orows * job.planes * 4, &p0))) return rc;
+		const long long tps = (long long)P * orows;
 		if (both1) {
-			void *p0; if ((rc = morsi_ws_get(c, job.lane, 0, (size_t)P * orows * job.planes * 4, &p0))) return rc;
-			const long long tps = (long long)P * orows;
 			rc = disk_pass(c, id, false, EPI_A, job, xb, job.x_rows, none, none, (float *)p0, tps, o0, orows, flag);
 			if (rc) return rc;
 			rc = disk_pass(c, id, true, plan.epi, job, xb, job.x_rows, xb, Band{(float *)p0, o0, tps},
@@ -906,28 +1233,18 @@ static int run_disk_passes(MorsiCtx *c, int id, const DevElement *de, const Mors
 			if (rc) return rc;
 			continue;
 		}
-		// oscillation = closing - opening: erosion and dilation of x, then the
-		// opposite reductions, the last one subtracting
-		int t0 = o0 - R; if (t0 < 0) t0 = 0;
-		int t1 = o0 + orows + R; if (t1 > job.h) t1 = job.h;
-		const int trows = t1 - t0;
-		const long long tps = (long long)P * trows;
-		const size_t tbytes = (size_t)tps * job.planes * 4;
-		void *p0, *p1, *p2;
-		if ((rc = morsi_ws_get(c, job.lane, 0, tbytes, &p0))) return rc;
-		if ((rc = morsi_ws_get(c, job.lane, 1, tbytes, &p1))) return rc;
-		if ((rc = morsi_ws_get(c, job.lane, 2, (size_t)P * orows * job.planes * 4, &p2))) return rc;
-		const long long ops = (long long)P * orows;
-		rc = disk_pass(c, id, false, EPI_A, job, xb, job.x_rows, none, none, (float *)p0, tps, t0, trows, flag);
-		if (rc) return rc;
-		rc = disk_pass(c, id, true, EPI_B, job, xb, job.x_rows, none, none, (float *)p1, tps, t0, trows, flag);
-		if (rc) return rc;
-		rc = disk_pass(c, id, true, EPI_B, job, Band{(float *)p0, t0, tps}, trows, none, none,
-				(float *)p2, ops, o0, orows, flag);
-		if (rc) return rc;
-		rc = disk_pass(c, id, false, EPI_A_SUB_B, job, Band{(float *)p1, t0, tps}, trows, none,
-				Band{(float *)p2, o0, ops}, ydst, job.y_pstride, o0, orows, flag);
-		if (rc) return rc;
+		// oscillation = closing - opening (src/morsi.c:217-227): the fused closing into the
+		// temporary, then the fused opening with the closing as the operand its epilogue
+		// subtracts from (the tophat kernel, x := closing): two launches, one temporary
+		DiskArgs a;
+		a.src = xb; a.src_rows = job.x_rows; a.other = none; a.xop = none;
+		a.y = (float *)p0; a.y_pstride = tps; a.y_row0 = o0; a.y_rows = orows;
+		a.w = job.w; a.h = job.h; a.epi = EPI_A; a.flag = flag; a.band_rows = orows;
+		a.pitch = P;
+		if ((rc = launch_by_id(id, c, a, job.planes, true, true, job.stream))) return rc;       // closing
+		a.xop = Band{(float *)p0, o0, tps};
+		a.y = ydst; a.y_pstride = job.y_pstride; a.epi = EPI_X_SUB_B;
+		if ((rc = launch_by_id(id, c, a, job.planes, false, true, job.stream))) return rc;      // closing - opening
 	}
 	return MORSI_OK;
 }

@@ -63,6 +63,7 @@ struct morsi_shard {
 	char *peer[2];                 // neighbours' slabs in this process' address space (0: up, 1: down)
 	bool peer_ipc[2];
 	int peer_i0[2];                // first held row of the neighbour
+	size_t peer_buf_bytes[2];      // size of one of ITS buffers (bands differ by a row when h % N != 0)
 	unsigned step;
 	cudaStream_t stream, s_in, s_out, s_comm;
 	cudaEvent_t ev[4];
@@ -176,7 +177,9 @@ __global__ void k_shard_wait(unsigned *ready_up, unsigned *ready_down, unsigned 
 		"shard: %s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
 static inline unsigned *flag_of(char *slab, int word) { return (unsigned *)slab + word; }
+static inline size_t band_buf_bytes(int held_rows, int w) { return ((size_t)held_rows * w * sizeof(float) + 255) & ~(size_t)255; }
 static inline float *buf_of(const morsi_shard *s, char *slab, int b) { return (float *)(slab + SHARD_FLAG_BYTES + (size_t)b * s->buf_bytes); }
+static inline float *peer_buf_of(const morsi_shard *s, int k, int b) { return (float *)(s->peer[k] + SHARD_FLAG_BYTES + (size_t)b * s->peer_buf_bytes[k]); }
 
 extern "C" int morsi_shard_create(morsi_shard **out, int device, int rank, int nranks, int w, int h, int halo_rows, int nbuf)
 {
@@ -192,7 +195,7 @@ extern "C" int morsi_shard_create(morsi_shard **out, int device, int rank, int n
 	s->ctx = c;
 	s->b0 = band_first(h, rank, nranks); s->b1 = band_first(h, rank + 1, nranks);
 	s->i0 = std::max(0, s->b0 - halo_rows); s->i1 = std::min(h, s->b1 + halo_rows);
-	s->buf_bytes = ((size_t)(s->i1 - s->i0) * w * sizeof(float) + 255) & ~(size_t)255;
+	s->buf_bytes = band_buf_bytes(s->i1 - s->i0, w);
 	s->slab_bytes = SHARD_FLAG_BYTES + (size_t)nbuf * s->buf_bytes;
 	s->peer[0] = s->peer[1] = nullptr; s->peer_ipc[0] = s->peer_ipc[1] = false;
 	s->step = 0;
@@ -268,6 +271,9 @@ extern "C" int morsi_shard_connect(morsi_shard *s, const void *handles)
 			s->peer_ipc[k] = true;
 		}
 		s->peer_i0[k] = std::max(0, band_first(s->h, nb, s->nranks) - s->halo);
+		s->peer_buf_bytes[k] = band_buf_bytes(std::min(s->h, band_first(s->h, nb + 1, s->nranks) + s->halo) - s->peer_i0[k], s->w);
+		if (SHARD_FLAG_BYTES + (size_t)s->nbuf * s->peer_buf_bytes[k] != hd.slab_bytes)
+			return morsi_set_error(MORSI_ERR_COMM, "shard_connect: rank %d's slab is %llu bytes, expected %zu", nb, hd.slab_bytes, SHARD_FLAG_BYTES + (size_t)s->nbuf * s->peer_buf_bytes[k]);
 	}
 	return MORSI_OK;
 }
@@ -320,7 +326,7 @@ static int shard_push(morsi_shard *s, int src, int up, int down, cudaEvent_t aft
 		// my first `down` rows are the upper neighbour's bottom halo
 		const int n = std::min(down, own);
 		a.src[0] = mine + (size_t)(s->b0 - s->i0) * s->w;
-		a.dst[0] = buf_of(s, s->peer[0], src) + (size_t)(s->b0 - s->peer_i0[0]) * s->w;
+		a.dst[0] = peer_buf_of(s, 0, src) + (size_t)(s->b0 - s->peer_i0[0]) * s->w;
 		a.n[0] = (long long)n * s->w;
 		a.peer_ready[0] = flag_of(s->peer[0], F_READY_DOWN);
 		a.peer_done[0] = flag_of(s->peer[0], F_DONE_DOWN);
@@ -330,7 +336,7 @@ static int shard_push(morsi_shard *s, int src, int up, int down, cudaEvent_t aft
 		if (!s->peer[1]) return morsi_set_error(MORSI_ERR_COMM, "shard_apply: rank %d is not connected (morsi_shard_connect)", s->rank);
 		const int n = std::min(up, own);
 		a.src[1] = mine + (size_t)(s->b1 - n - s->i0) * s->w;
-		a.dst[1] = buf_of(s, s->peer[1], src) + (size_t)(s->b1 - n - s->peer_i0[1]) * s->w;
+		a.dst[1] = peer_buf_of(s, 1, src) + (size_t)(s->b1 - n - s->peer_i0[1]) * s->w;
 		a.n[1] = (long long)n * s->w;
 		a.peer_ready[1] = flag_of(s->peer[1], F_READY_UP);
 		a.peer_done[1] = flag_of(s->peer[1], F_DONE_UP);
