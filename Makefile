@@ -15,7 +15,7 @@ CU_SRCS := $(wildcard $(SRC)/*.cu)
 CU_OBJS := $(patsubst $(SRC)/%.cu,$(OBJ)/%.o,$(CU_SRCS)) $(OBJ)/k_disk_p1.o $(OBJ)/k_disk_p2.o $(OBJ)/k_disk_p3.o
 HDRS    := $(wildcard $(SRC)/*.cuh) $(wildcard $(SRC)/*.h) include/morsi_cuda.h
 
-all: $(OUT)/libmorsi_cuda.so $(OUT)/libmorsi_compat.so cli
+all: $(OUT)/libmorsi_cuda.so $(OUT)/libmorsi_compat.so cli $(OUT)/compat_caller
 
 $(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
 	@mkdir -p $(OBJ)
@@ -37,10 +37,18 @@ $(OUT)/libmorsi_cuda.so: $(CU_OBJS) $(OBJ)/element.o
 $(OUT)/libmorsi_compat.so: $(SRC)/compat.c $(OUT)/libmorsi_cuda.so
 	$(CC) -O2 -fPIC -Wall -shared -o $@ $(SRC)/compat.c -L$(OUT) -lmorsi_cuda -Wl,-rpath,'$$ORIGIN'
 
+# a library-style caller of the reference API (tests/c/compat_caller.c), linked the way
+# INTEGRATION.md tells a maintainer to relink corrview.c: -lmorsi_compat -lmorsi_cuda
+$(OUT)/compat_caller: tests/c/compat_caller.c $(OUT)/libmorsi_compat.so
+	$(CC) -O2 -Wall -o $@ tests/c/compat_caller.c -L$(OUT) -lmorsi_compat -lmorsi_cuda -Wl,-rpath,'$$ORIGIN'
+
 # The CLI keeps the reference's image I/O: iio.c is compiled from the reference
 # tree (never copied).  Where the tree is absent the prebuilt binary is kept.
 ifneq ($(wildcard $(REF)/src/iio.c),)
-cli: $(OUT)/morsi
+cli: $(OUT)/morsi $(OUT)/im_like
+# the multi-call form of src/im.c:4-6: morsi_main.c with its main hidden
+$(OUT)/im_like: tests/c/im_like.c $(SRC)/morsi_main.c $(OBJ)/iio.o $(OUT)/libmorsi_cuda.so
+	$(CC) -O2 -Wall -DHIDE_ALL_MAINS -o $@ tests/c/im_like.c $(SRC)/morsi_main.c $(OBJ)/iio.o -L$(OUT) -lmorsi_cuda -lm -Wl,-rpath,'$$ORIGIN'
 $(OBJ)/iio.o: $(REF)/src/iio.c
 	@mkdir -p $(OBJ)
 	$(CC) -O3 -w -c $< -o $@

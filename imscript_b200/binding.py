@@ -24,12 +24,15 @@ EXPORTED_SYMBOLS = [
     "morsi_cuda_event_elapsed_ms", "morsi_cuda_event_destroy",
     "morsi_shard_create", "morsi_shard_handle", "morsi_shard_connect", "morsi_shard_rows",
     "morsi_shard_buffer", "morsi_shard_stream", "morsi_shard_apply", "morsi_shard_apply_host",
+    "morsi_cuda_apply_all_device", "morsi_cuda_apply_interleaved", "morsi_cuda_apply_stream",
     "morsi_shard_exchange", "morsi_cuda_stream_create", "morsi_cuda_stream_destroy",
     "morsi_shard_sync", "morsi_shard_halo_bytes", "morsi_shard_destroy", "morsi_cuda_apply_sharded",
 ]
 SHARD_HANDLE_BYTES = 128
 COMPAT_SYMBOLS = ["morsi_" + o for o in OPS] + ["morsi_all", "build_disk"]
 
+READ_ROWS_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p)
+WRITE_ROWS_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p)
 _f32p = ctypes.POINTER(ctypes.c_float)
 _i32p = ctypes.POINTER(ctypes.c_int)
 _vp = ctypes.c_void_p
@@ -99,6 +102,11 @@ def lib():
         L.morsi_cuda_event_record.argtypes = [_vp, _vp]
         L.morsi_cuda_event_elapsed_ms.argtypes = [_vp, _vp, ctypes.POINTER(ctypes.c_float)]
         L.morsi_cuda_event_destroy.argtypes = [_vp]
+        L.morsi_cuda_apply_all_device.argtypes = [_i32p, _vp, ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]
+        L.morsi_cuda_apply_interleaved.argtypes = [ctypes.c_int, _i32p, _vp, _vp, ctypes.c_int, ctypes.c_int,
+                                                   ctypes.c_int, ctypes.c_int]
+        L.morsi_cuda_apply_stream.argtypes = [ctypes.c_int, _i32p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              READ_ROWS_FN, WRITE_ROWS_FN, _vp]
         L.morsi_shard_create.argtypes = [ctypes.POINTER(_vp)] + [ctypes.c_int] * 7
         L.morsi_shard_handle.argtypes = [_vp, _vp]
         L.morsi_shard_connect.argtypes = [_vp, _vp]
@@ -252,6 +260,42 @@ def apply_band_device(op, e, d_x, x_row0, x_rows, d_y, y_row0, y_rows, w, h, str
                                              py, y_row0, y_rows, w, h, stream))
     if sync:
         check(lib().morsi_cuda_sync(stream))
+
+
+def apply_interleaved(op, e, x):
+    """x: (h, w, pd) uint8 / uint16 / float32, pixel-interleaved -> (h, w, pd) float32."""
+    e = _e(e)
+    x = np.ascontiguousarray(x)
+    if x.ndim == 2:
+        x = x[:, :, None]
+    t = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2}[x.dtype]
+    h, w, pd = x.shape
+    y = np.empty((h, w, pd), np.float32)
+    check(lib().morsi_cuda_apply_interleaved(_op(op), e.ctypes.data_as(_i32p), x.ctypes.data, y.ctypes.data, w, h, pd, t))
+    return y
+
+
+def apply_stream(op, e, w, h, planes, read_rows, write_rows):
+    """read_rows(plane, row0, nrows) -> (nrows, w) float32 array; write_rows(plane, row0, rows_array)."""
+    e = _e(e)
+
+    def rd(user, plane, row0, nrows, dst):
+        try:
+            a = np.ascontiguousarray(read_rows(plane, row0, nrows), dtype=np.float32)
+            ctypes.memmove(dst, a.ctypes.data, a.nbytes)
+            return 0
+        except Exception:
+            return 1
+
+    def wr(user, plane, row0, nrows, src):
+        try:
+            a = np.ctypeslib.as_array(ctypes.cast(src, _f32p), shape=(nrows, w)).copy()
+            write_rows(plane, row0, a)
+            return 0
+        except Exception:
+            return 1
+    check(lib().morsi_cuda_apply_stream(_op(op), e.ctypes.data_as(_i32p), w, h, planes,
+                                        READ_ROWS_FN(rd), WRITE_ROWS_FN(wr), None))
 
 
 def apply_sharded(op, e, x, ndev, iterations=1):

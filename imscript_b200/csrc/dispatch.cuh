@@ -11,7 +11,8 @@
 #include "element.h"
 
 #define MORSI_WS_SLOTS 10  // 0-3: kernel temporaries, 4-5: host-pipeline staging, 6-7: pitched copies (k_disk), 8-9: morsi_all results
-#define MORSI_LANES 4   // lane 0: the *_device entry points; 1..3: host-pointer pipeline
+#define MORSI_LANES 5   // lane 0: the *_device entry points; 1..3: host-pointer pipeline; 4: edge strips of a sharded band
+#define MORSI_LANE_SHARD_SIDE 4
 
 // compiled form of a row-run element (k_rowrun.cu)
 struct RowRunPlan {

@@ -10,6 +10,7 @@
 // needed on this entry point.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -17,6 +18,26 @@
 #include "dispatch.cuh"
 
 struct Chunk { int plane, r0, r1; };
+
+// A caller's malloc'd (pageable) image: cudaMemcpyAsync would stage it through the
+// driver synchronously and the three-lane overlap would be lost.  Page-lock it
+// for the duration of the call instead (the reference CLI's buffers come from
+// iio's malloc, src/morsi.c:531-532).  Already pinned / registered memory and
+// small images are left alone; a failed registration only costs the overlap.
+struct HostPin {
+	void *p = nullptr;
+	HostPin(const void *ptr, size_t bytes)
+	{
+		static const bool off = getenv("MORSI_CUDA_HOST_REGISTER") && !strcmp(getenv("MORSI_CUDA_HOST_REGISTER"), "0");
+		if (off || bytes < (8u << 20)) return;
+		cudaPointerAttributes at;
+		if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return; }
+		if (at.type != cudaMemoryTypeUnregistered) return;
+		if (cudaHostRegister((void *)ptr, bytes, cudaHostRegisterPortable) == cudaSuccess) p = (void *)ptr;
+		else cudaGetLastError();
+	}
+	~HostPin() { if (p) cudaHostUnregister(p); }
+};
 
 static int run_chunks(int device, int op, const int *e, const float *x, float *y,
 		int w, int h, const std::vector<Chunk> &chunks, int up, int down)
@@ -80,6 +101,7 @@ extern "C" int morsi_cuda_apply(int op, const int *e, const float *x, float *y,
 	int up = 0, down = 0;
 	int rc = morsi_cuda_halo_rows(op, e, &up, &down);
 	if (rc) return rc;
+	HostPin pin_x(x, (size_t)w * h * planes * sizeof(float)), pin_y(y, (size_t)w * h * planes * sizeof(float));
 
 	// chunk height: ~32 MiB of input per chunk, at least 8x the halo
 	long long target = (32LL << 20) / ((long long)w * 4);   // 32 MiB: C2 e2e 10.15 vs 9.94 Gpixel/s with 16 MiB (PCIe ceiling of the box: 47.9 GB/s per direction, both busy)
@@ -119,64 +141,3 @@ extern "C" int morsi_cuda_apply(int op, const int *e, const float *x, float *y,
 	return MORSI_OK;
 }
 
-// ---------------------------------------------------------------------------
-// morsi_all (src/morsi.c:278-310): up to 12 results of ONE input.  The input
-// crosses PCIe once and stays resident; every requested output is one (fused)
-// device operation into one of two result buffers, copied back on a second
-// stream while the next operation runs.  Values equal the single-operation
-// results (the reference's shared temporaries change no value; its laplacian
-// adds max+min instead of min+max, and float addition commutes).
-// ---------------------------------------------------------------------------
-extern "C" int morsi_cuda_apply_all(const int *e, const float *x, float *const out[12], int w, int h, int planes)
-{
-	static const int ops[12] = {MORSI_EROSION, MORSI_DILATION, MORSI_OPENING, MORSI_CLOSING, MORSI_GRADIENT,
-		MORSI_IGRADIENT, MORSI_EGRADIENT, MORSI_LAPLACIAN, MORSI_ENHANCE, MORSI_OSCILLATION, MORSI_TOPHAT, MORSI_BOTHAT};
-	if (!e || e[0] < 0) return morsi_set_error(MORSI_ERR_INVALID, "bad structuring element");
-	if (!x || !out) return morsi_set_error(MORSI_ERR_INVALID, "NULL image pointer");
-	if (w <= 0 || h <= 0 || planes <= 0)
-		return morsi_set_error(MORSI_ERR_INVALID, "non-positive image size %dx%dx%d", w, h, planes);
-	MorsiCtx *c;
-	int rc = morsi_ctx_current(&c);
-	if (rc) return rc;
-	std::lock_guard<std::mutex> host_lk(c->host_mu);
-	const size_t bytes = (size_t)w * h * planes * sizeof(float);
-	void *d_x, *d_y[2];
-	if ((rc = morsi_ws_get(c, 1, 4, bytes, &d_x))) return rc;
-	// all three on lane 1: stream-ordered allocations belong to the stream that runs the kernels
-	if ((rc = morsi_ws_get(c, 1, 8, bytes, &d_y[0]))) return rc;
-	if ((rc = morsi_ws_get(c, 1, 9, bytes, &d_y[1]))) return rc;
-	cudaStream_t s_run = c->lane_stream[1], s_copy = c->lane_stream[2];
-	cudaEvent_t done[2], freed[2];
-	for (int i = 0; i < 2; i++) {
-		MORSI_CU(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-		MORSI_CU(cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming));
-	}
-	MORSI_CU(cudaMemcpyAsync(d_x, x, bytes, cudaMemcpyHostToDevice, s_run));
-	int used = 0;
-	for (int k = 0; k < 12 && !rc; k++) {
-		if (!out[k]) continue;
-		const int b = used & 1;
-		if (used >= 2) MORSI_CU(cudaStreamWaitEvent(s_run, freed[b], 0));   // its previous result has left
-		MorsiJob job;
-		job.op = ops[k]; job.w = w; job.h = h; job.lane = 1;
-		job.x_row0 = 0; job.x_rows = h; job.x_pstride = (long long)w * h;
-		job.y_row0 = 0; job.y_rows = h; job.y_pstride = (long long)w * h;
-		job.stream = s_run;
-		for (int p0 = 0; p0 < planes && !rc; p0 += 32768) {
-			job.planes = planes - p0 < 32768 ? planes - p0 : 32768;
-			job.x = (const float *)d_x + (long long)p0 * w * h;
-			job.y = (float *)d_y[b] + (long long)p0 * w * h;
-			rc = morsi_dispatch(c, e, job);
-		}
-		if (rc) break;
-		MORSI_CU(cudaEventRecord(done[b], s_run));
-		MORSI_CU(cudaStreamWaitEvent(s_copy, done[b], 0));
-		MORSI_CU(cudaMemcpyAsync(out[k], d_y[b], bytes, cudaMemcpyDeviceToHost, s_copy));
-		MORSI_CU(cudaEventRecord(freed[b], s_copy));
-		used++;
-	}
-	cudaStreamSynchronize(s_run);
-	cudaStreamSynchronize(s_copy);
-	for (int i = 0; i < 2; i++) { cudaEventDestroy(done[i]); cudaEventDestroy(freed[i]); }
-	return rc;
-}

@@ -170,7 +170,7 @@ extern "C" void morsi_cuda_shutdown(void)
 		for (auto &e : c->elements) { cudaFree(e.second.d_offs); cudaFree(e.second.d_tile_offs); }
 		for (int l = 0; l < MORSI_LANES; l++)
 			for (int i = 0; i < MORSI_WS_SLOTS; i++)
-				if (c->ws[l][i]) { if (l > 0) cudaFreeAsync(c->ws[l][i], c->lane_stream[l]); else cudaFree(c->ws[l][i]); }
+				if (c->ws[l][i]) { if (l >= 1 && l <= 3) cudaFreeAsync(c->ws[l][i], c->lane_stream[l]); else cudaFree(c->ws[l][i]); }
 		for (int l = 0; l < MORSI_LANES; l++) if (c->lane_stream[l]) cudaStreamSynchronize(c->lane_stream[l]);
 		for (int l = 0; l < MORSI_LANES; l++) if (c->lane_stream[l]) cudaStreamDestroy(c->lane_stream[l]);
 		cudaFree(c->d_flag);
@@ -191,7 +191,7 @@ int morsi_ws_get(MorsiCtx *c, int lane, int slot, size_t bytes, void **out)
 {
 	std::lock_guard<std::mutex> lk(c->mu);
 	if (c->ws_bytes[lane][slot] < bytes) {
-		const bool async = lane > 0;
+		const bool async = lane >= 1 && lane <= 3;
 		if (c->ws[lane][slot]) {
 			if (async) CU(cudaFreeAsync(c->ws[lane][slot], c->lane_stream[lane]));
 			else { CU(cudaDeviceSynchronize()); CU(cudaFree(c->ws[lane][slot])); }

@@ -9,9 +9,11 @@
  * library instead of the per-channel function-pointer loop (:539-543).
  * No GPU => error exit; there is no CPU fallback.
  */
+#define _FILE_OFFSET_BITS 64
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/types.h>
 
 #include "../../include/morsi_cuda.h"
 
@@ -105,6 +107,118 @@ static void handle_help_argument(const char *s)
 	if (!strcmp(s, "--help-oneliner")) puts(oneliner);   /* falls through to the usage error */
 }
 
+static void die(const char *prog, int rc)
+{
+	fprintf(stderr, "FAIL(\"%s\"): libmorsi_cuda: %s: %s\n", prog,
+			morsi_cuda_strerror(rc), morsi_cuda_last_error());
+	exit(-1);
+}
+
+/* ---- extension 1: `morsi ELEMENT all in out-%s.ext` ------------------------
+ * The twelve results of morsi_all (src/morsi.c:278-310) from one read of the
+ * input and one upload, written to the output name with %s replaced by the
+ * operation's name (the tutorial, doc/tutorial/i.html:213-225, runs morsi 13
+ * times on the same image for this).  "all" is not a name of the reference's
+ * operation table, so no reference invocation changes meaning. */
+static int run_all(const char *prog, int *element, const char *in, const char *out)
+{
+	static const char *const names[12] = {"erosion", "dilation", "opening", "closing", "gradient", "igradient",
+		"egradient", "laplacian", "enhance", "oscillation", "tophat", "bothat"};
+	const char *pct = strstr(out, "%s");
+	if (!pct || strstr(pct + 2, "%")) {
+		fprintf(stderr, "usage:\n\t%s element all in out-%%s.ext\n", prog);
+		return 1;
+	}
+	int w, h, pd;
+	float *x = iio_read_image_float_split(in, &w, &h, &pd);
+	size_t n = (size_t)w * h * pd;
+	float *y[12];
+	for (int k = 0; k < 12; k++)
+		if (morsi_cuda_host_alloc((void **)&y[k], n * sizeof(float)) != MORSI_OK) {
+			fprintf(stderr, "FAIL(\"%s\"): out of memory\n", prog);
+			exit(-1);
+		}
+	int rc = morsi_cuda_apply_all(element, x, y, w, h, pd);
+	if (rc != MORSI_OK) die(prog, rc);
+	for (int k = 0; k < 12; k++) {
+		char name[0x400];
+		snprintf(name, sizeof name, "%.*s%s%s", (int)(pct - out), out, names[k], pct + 2);
+		iio_write_image_float_split(name, y[k], w, h, pd);
+		morsi_cuda_host_free(y[k]);
+	}
+	free(x);
+	return 0;
+}
+
+/* ---- extension 2: MORSI_CUDA_STREAM=1, float32 2-D .npy in and out ----------
+ * The image streams from the input file through the device to the output file
+ * in row bands (morsi_cuda_apply_stream): the host never holds it, so planes
+ * larger than memory -- and than the int-sized buffers of src/iio.c:3759,4073 --
+ * go through.  Anything else falls back to the ordinary path. */
+struct npy_io { FILE *in, *out; long in_off, out_off; int w; };
+static int npy_read_rows(void *u, int plane, int row0, int nrows, float *dst)
+{
+	struct npy_io *io = u;
+	(void)plane;
+	if (fseeko(io->in, io->in_off + (off_t)row0 * io->w * 4, SEEK_SET)) return 1;
+	return fread(dst, 4, (size_t)nrows * io->w, io->in) != (size_t)nrows * io->w;
+}
+static int npy_write_rows(void *u, int plane, int row0, int nrows, const float *src)
+{
+	struct npy_io *io = u;
+	(void)plane;
+	if (fseeko(io->out, io->out_off + (off_t)row0 * io->w * 4, SEEK_SET)) return 1;
+	return fwrite(src, 4, (size_t)nrows * io->w, io->out) != (size_t)nrows * io->w;
+}
+/* 0: streamed; -1: not applicable (caller takes the ordinary path) */
+static int try_stream_npy(const char *prog, int op, int *element, const char *in, const char *out)
+{
+	const char *s = getenv("MORSI_CUDA_STREAM");
+	size_t li = strlen(in), lo = strlen(out);
+	if (!s || strcmp(s, "1") || li < 5 || lo < 5 || strcmp(in + li - 4, ".npy") || strcmp(out + lo - 4, ".npy"))
+		return -1;
+	FILE *f = fopen(in, "rb");
+	if (!f) return -1;
+	unsigned char hd[10];
+	char dict[4096];
+	if (fread(hd, 1, 10, f) != 10 || memcmp(hd, "\x93NUMPY", 6) || hd[6] != 1) { fclose(f); return -1; }
+	unsigned hlen = hd[8] | (hd[9] << 8);
+	if (hlen >= sizeof dict || fread(dict, 1, hlen, f) != hlen) { fclose(f); return -1; }
+	dict[hlen] = 0;
+	long hh = 0, ww = 0;
+	const char *sh = strstr(dict, "'shape'");
+	if (!strstr(dict, "'<f4'") || !strstr(dict, "False") || !sh || sscanf(sh, "'shape': (%ld, %ld)", &hh, &ww) != 2
+			|| hh <= 0 || ww <= 0 || hh > 0x7fffffff || ww > 0x7fffffff) { fclose(f); return -1; }
+	/* exactly two dimensions: no second comma before the closing parenthesis */
+	{
+		const char *p0 = strchr(sh, '('), *p1 = strchr(sh, ')');
+		int commas = 0;
+		for (const char *q = p0; q && p1 && q < p1; q++) commas += *q == ',';
+		if (commas != 1) { fclose(f); return -1; }
+	}
+	FILE *g = fopen(out, "wb");
+	if (!g) { fclose(f); return -1; }
+	char oh[128];
+	int n = snprintf(oh, sizeof oh, "{'descr': '<f4', 'fortran_order': False, 'shape': (%ld, %ld), }", hh, ww);
+	int total = (10 + n + 1 + 63) / 64 * 64;            /* header padded to 64 bytes, newline last */
+	unsigned char ohd[10] = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0, 0, 0};
+	ohd[8] = (total - 10) & 255; ohd[9] = (total - 10) >> 8;
+	fwrite(ohd, 1, 10, g);
+	fwrite(oh, 1, n, g);
+	for (int k = 10 + n; k < total - 1; k++) fputc(' ', g);
+	fputc('\n', g);
+	struct npy_io io = {f, g, 10 + (long)hlen, total, (int)ww};
+	int rc = morsi_cuda_apply_stream(op, element, (int)ww, (int)hh, 1, npy_read_rows, npy_write_rows, &io);
+	fclose(f);
+	if (fclose(g)) rc = rc ? rc : MORSI_ERR_INVALID;
+	if (rc != MORSI_OK) die(prog, rc);
+	return 0;
+}
+
+/* the iio "vec" entry points (src/iio.h:33,176): pixel-interleaved samples */
+float *iio_read_image_float_vec(const char *fname, int *w, int *h, int *pd);
+void iio_write_image_float_vec(char *fname, float *x, int w, int h, int pd);
+
 int main_morsi(int c, char **v)
 {
 	if (c == 2) handle_help_argument(v[1]);
@@ -121,31 +235,41 @@ int main_morsi(int c, char **v)
 		fprintf(stderr, "elements = cross, square ...\n");
 		return 1;
 	}
+	if (!strcmp(v[2], "all") && c == 5)
+		return run_all(*v, element, filename_in, filename_out);
 	int op = morsi_operation_parse(v[2]);
 	if (op < 0) {
 		fprintf(stderr, "operations = erosion, dilation, opening...\n");
 		return 1;
 	}
+	if (try_stream_npy(*v, op, element, filename_in, filename_out) == 0)
+		return 0;
 
+	/* The reference reads with iio_read_image_float_split (src/morsi.c:531): a
+	 * "vec" read followed by a CPU pass that splits the pixels into planes
+	 * (src/iio.c:5763-5771), and joins them again on the way out (:6525-6531).
+	 * Here the vec image goes to the device as it is and is split / joined
+	 * there (MORSI_CUDA_SPLIT=host restores the CPU passes). */
 	int w, h, pd;
-	float *x = iio_read_image_float_split(filename_in, &w, &h, &pd);
-	float *y = malloc((size_t)w * h * pd * sizeof *y);
-	if (!y) {
+	const char *sp = getenv("MORSI_CUDA_SPLIT");
+	const int split_on_host = sp && !strcmp(sp, "host");
+	float *x = split_on_host ? iio_read_image_float_split(filename_in, &w, &h, &pd)
+		: iio_read_image_float_vec(filename_in, &w, &h, &pd);
+	float *y = NULL;
+	if (morsi_cuda_host_alloc((void **)&y, (size_t)w * h * pd * sizeof *y) != MORSI_OK) {   /* page-locked: the download overlaps */
 		fprintf(stderr, "FAIL(\"%s\"): out of memory\n", *v);
 		exit(-1);
 	}
 
-	int rc = morsi_cuda_apply(op, element, x, y, w, h, pd);
-	if (rc != MORSI_OK) {
-		fprintf(stderr, "FAIL(\"%s\"): libmorsi_cuda: %s: %s\n", *v,
-				morsi_cuda_strerror(rc), morsi_cuda_last_error());
-		exit(-1);
-	}
+	int rc = (split_on_host || pd == 1) ? morsi_cuda_apply(op, element, x, y, w, h, pd)
+		: morsi_cuda_apply_interleaved(op, element, x, y, w, h, pd, MORSI_SAMPLE_F32);
+	if (rc != MORSI_OK) die(*v, rc);
 
-	iio_write_image_float_split(filename_out, y, w, h, pd);
+	if (split_on_host) iio_write_image_float_split(filename_out, y, w, h, pd);
+	else iio_write_image_float_vec(filename_out, y, w, h, pd);
 
 	free(x);
-	free(y);
+	morsi_cuda_host_free(y);
 	return 0;
 }
 

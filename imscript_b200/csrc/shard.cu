@@ -21,7 +21,8 @@
 //                  right behind the push, so the transfer hides behind them;
 //   k_shard_wait   spins (a single thread) on this rank's two ready words;
 //   kernels        the two edge strips.
-// Everything is stream-ordered on the rank's own stream: no host
+// Everything is stream-ordered on the rank's own streams (main: interior rows; communication:
+// the push; side: the halo wait and the edge strips): no host
 // synchronisation, no collective, no reduction -- the path only has this
 // point-to-point exchange.  The reference has no counterpart (one thread, one
 // process); the rows needed per stage follow src/morsi.c:65, the border rule
@@ -65,7 +66,7 @@ struct morsi_shard {
 	int peer_i0[2];                // first held row of the neighbour
 	size_t peer_buf_bytes[2];      // size of one of ITS buffers (bands differ by a row when h % N != 0)
 	unsigned step;
-	cudaStream_t stream, s_in, s_out, s_comm;
+	cudaStream_t stream, s_in, s_out, s_comm, s_side;
 	cudaEvent_t ev[4];
 	std::vector<cudaEvent_t> ev_chunks;
 	int overlap;                   // 1: interior rows first, edge strips after the halo (default)
@@ -214,6 +215,7 @@ extern "C" int morsi_shard_create(morsi_shard **out, int device, int rank, int n
 	SH_CU(cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
 	SH_CU(cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
 	SH_CU(cudaStreamCreateWithFlags(&s->s_comm, cudaStreamNonBlocking));
+	SH_CU(cudaStreamCreateWithFlags(&s->s_side, cudaStreamNonBlocking));
 	for (int i = 0; i < 4; i++) SH_CU(cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming));
 	*out = s;
 	return MORSI_OK;
@@ -296,11 +298,11 @@ extern "C" float *morsi_shard_buffer(morsi_shard *s, int buf)
 extern "C" void *morsi_shard_stream(morsi_shard *s) { return s ? (void *)s->stream : nullptr; }
 extern "C" long long morsi_shard_halo_bytes(const morsi_shard *s) { return s ? s->halo_bytes_last : 0; }
 
-static int shard_job(morsi_shard *s, int op, const int *e, int src, int dst, int r0, int r1, cudaStream_t st)
+static int shard_job(morsi_shard *s, int op, const int *e, int src, int dst, int r0, int r1, cudaStream_t st, int lane = 0)
 {
 	if (r1 <= r0) return MORSI_OK;
 	MorsiJob job;
-	job.op = op; job.w = s->w; job.h = s->h; job.planes = 1; job.lane = 0;
+	job.op = op; job.w = s->w; job.h = s->h; job.planes = 1; job.lane = lane;
 	job.x = buf_of(s, s->slab, src); job.x_row0 = s->i0; job.x_rows = s->i1 - s->i0; job.x_pstride = (long long)s->w * (s->i1 - s->i0);
 	job.y = buf_of(s, s->slab, dst) + (size_t)(r0 - s->i0) * s->w; job.y_row0 = r0; job.y_rows = r1 - r0;
 	job.y_pstride = (long long)s->w * (s->i1 - s->i0);
@@ -390,10 +392,16 @@ extern "C" int morsi_shard_apply(morsi_shard *s, int op, const int *e, int src, 
 	const int top = s->rank > 0 ? up : 0, bot = s->rank < s->nranks - 1 ? down : 0;
 	const int own = s->b1 - s->b0;
 	if (s->overlap && s->nranks > 1 && own > 4 * (top + bot) + 64) {
+		// interior rows on the main stream; the halo wait and the two edge strips on a side
+		// stream (its own flag / workspace lane), so that the strips start the moment the halo
+		// has landed and fill the SMs the interior's last wave leaves idle
+		SH_CU(cudaStreamWaitEvent(s->s_side, s->ev[2], 0));
 		if ((rc = shard_job(s, op, e, src, dst, s->b0 + top, s->b1 - bot, s->stream))) return rc;
-		if ((rc = shard_wait(s, s->stream))) return rc;
-		if ((rc = shard_job(s, op, e, src, dst, s->b0, s->b0 + top, s->stream))) return rc;
-		if ((rc = shard_job(s, op, e, src, dst, s->b1 - bot, s->b1, s->stream))) return rc;
+		if ((rc = shard_wait(s, s->s_side))) return rc;
+		if ((rc = shard_job(s, op, e, src, dst, s->b0, s->b0 + top, s->s_side, MORSI_LANE_SHARD_SIDE))) return rc;
+		if ((rc = shard_job(s, op, e, src, dst, s->b1 - bot, s->b1, s->s_side, MORSI_LANE_SHARD_SIDE))) return rc;
+		SH_CU(cudaEventRecord(s->ev[3], s->s_side));
+		SH_CU(cudaStreamWaitEvent(s->stream, s->ev[3], 0));
 	} else {
 		if ((rc = shard_wait(s, s->stream))) return rc;
 		if ((rc = shard_job(s, op, e, src, dst, s->b0, s->b1, s->stream))) return rc;
@@ -423,6 +431,7 @@ extern "C" int morsi_shard_sync(morsi_shard *s)
 	SH_CU(cudaStreamSynchronize(s->s_in));
 	SH_CU(cudaStreamSynchronize(s->s_out));
 	SH_CU(cudaStreamSynchronize(s->s_comm));
+	SH_CU(cudaStreamSynchronize(s->s_side));
 	unsigned err = 0;
 	SH_CU(cudaMemcpy(&err, flag_of(s->slab, F_ERR), sizeof err, cudaMemcpyDeviceToHost));
 	if (err)
@@ -493,10 +502,11 @@ extern "C" int morsi_shard_destroy(morsi_shard *s)
 	cudaStreamSynchronize(s->s_in);
 	cudaStreamSynchronize(s->s_out);
 	cudaStreamSynchronize(s->s_comm);
+	cudaStreamSynchronize(s->s_side);
 	for (int k = 0; k < 2; k++) if (s->peer[k] && s->peer_ipc[k]) cudaIpcCloseMemHandle(s->peer[k]);
 	for (int i = 0; i < 4; i++) cudaEventDestroy(s->ev[i]);
 	for (cudaEvent_t evn : s->ev_chunks) cudaEventDestroy(evn);
-	cudaStreamDestroy(s->stream); cudaStreamDestroy(s->s_in); cudaStreamDestroy(s->s_out); cudaStreamDestroy(s->s_comm);
+	cudaStreamDestroy(s->stream); cudaStreamDestroy(s->s_in); cudaStreamDestroy(s->s_out); cudaStreamDestroy(s->s_comm); cudaStreamDestroy(s->s_side);
 	cudaFree(s->slab);
 	delete s;
 	return MORSI_OK;

@@ -113,9 +113,36 @@ int morsi_cuda_apply(int op, const int *e, const float *x, float *y,
 /* morsi_all (src/morsi.c:278-310) for host pointers: out[] = {erosion, dilation,
  * opening, closing, gradient, igradient, egradient, laplacian, enhance,
  * oscillation ("o_str"), tophat, bothat}; NULL entries are skipped.  The input
- * is copied to the device once; every result equals the single operation's. */
+ * is copied to the device once; erosion and dilation are computed once and
+ * shared by every output exactly as the reference does (:289-295), the
+ * pointwise outputs (:296-303) come from one pass over them.  Every result
+ * equals the single operation's. */
 int morsi_cuda_apply_all(const int *e, const float *x, float *const out[12],
 		int w, int h, int planes);
+/* The same on device-resident planar data, asynchronous on `stream`. */
+int morsi_cuda_apply_all_device(const int *e, const float *d_x, float *const d_out[12],
+		int w, int h, int planes, void *stream);
+
+/* Pixel-interleaved images (iio's "vec" layout, sample c of pixel i at
+ * x[i*pd + c]): the conversion to float and the split into planes that
+ * iio_read_image_float_split does on the CPU (src/iio.c:1416-1428, 5763-5771;
+ * sample conversions :1139-1158) happen on the device, and so does the join
+ * on the way out (src/iio.c:1423, 6525-6531).  An 8-bit image crosses PCIe as
+ * bytes.  y receives float32 samples in the same interleaved layout. */
+enum morsi_sample_type { MORSI_SAMPLE_U8 = 0, MORSI_SAMPLE_U16 = 1, MORSI_SAMPLE_F32 = 2 };
+int morsi_cuda_apply_interleaved(int op, const int *e, const void *x, float *y,
+		int w, int h, int pd, int sample_type);
+
+/* Streaming: the image is pulled and pushed in row bands through callbacks, so
+ * neither the host nor the device ever holds it as a whole (the job
+ * src/fancy_image.h:40-70 does for the reference's tools; all sizes are
+ * size_t / long long here, unlike src/iio.c:3759,4073).  rd must fill dst with
+ * rows [row0,row0+nrows) of `plane` (row pitch w); wr receives finished rows,
+ * in order, plane by plane.  A non-zero return aborts with MORSI_ERR_INVALID. */
+typedef int (*morsi_read_rows_fn)(void *user, int plane, int row0, int nrows, float *dst);
+typedef int (*morsi_write_rows_fn)(void *user, int plane, int row0, int nrows, const float *src);
+int morsi_cuda_apply_stream(int op, const int *e, int w, int h, int planes,
+		morsi_read_rows_fn rd, morsi_write_rows_fn wr, void *user);
 
 /* Same computation on DEVICE-resident planar data (row pitch = w), enqueued on
  * `stream` (a cudaStream_t; NULL = the context's stream) of the current

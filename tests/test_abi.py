@@ -114,3 +114,14 @@ def test_cli_error_paths_match_reference(golden_dir):
         assert p.stderr.decode().replace(CLI, "morsi") == g["stderr"], key
         if "stdout" in g:
             assert p.stdout.decode() == g["stdout"], key
+
+
+def test_long_line_with_repeats_is_flagged():
+    """a one-row list of 100 offsets spanning 100 columns, one column repeated and one missing: the line
+    kernels must not take it for a contiguous run (round-1 advice)"""
+    offs = list(range(100))
+    offs[50] = 10                                   # column 50 missing, column 10 twice
+    e = np.array([100, 0, 0, 0] + [v for x in offs for v in (x, 0)], dtype=np.int32)
+    assert " dup" in M.describe_element(e)
+    clean = np.array([100, 0, 0, 0] + [v for x in range(100) for v in (x, 0)], dtype=np.int32)
+    assert " dup" not in M.describe_element(clean)

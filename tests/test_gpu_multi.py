@@ -90,3 +90,23 @@ def test_sharded_single_rank_and_errors():
     s = ctypes.c_void_p()
     assert L.morsi_shard_create(ctypes.byref(s), 0, 0, 4, 64, 40, 28, 2) == 1      # bands shorter than the halo
     assert L.morsi_shard_create(ctypes.byref(s), 0, 2, 2, 64, 400, 8, 2) == 1      # rank out of range
+
+
+@needs2
+def test_host_entry_point_on_two_devices_large_smem_kernels(monkeypatch):
+    """MORSI_CUDA_DEVICES=2 with elements whose kernels opt in to > 48 KB of dynamic shared memory
+    (hrec60: k_line, dysk12: k_tiled): the opt-in is per device (round-1 advice)"""
+    o = oracle()
+    x = np.stack([M.synth_host(700, 300, plane=p, seed=5) for p in range(2)])
+    want = {}
+    for name, op in [("hrec60", "dilation"), ("dysk12", "erosion"), ("disk5", "rank")]:
+        want[(name, op)] = M.apply(op, o.element(name), x)
+    monkeypatch.setenv("MORSI_CUDA_DEVICES", "2")
+    for (name, op), y in want.items():
+        assert_same(M.apply(op, o.element(name), x), y, f"2 devices {name} {op}")
+    one = M.synth_host(700, 900, seed=6)
+    e = o.element("hrec60")
+    monkeypatch.delenv("MORSI_CUDA_DEVICES")
+    y1 = M.apply("opening", e, one)
+    monkeypatch.setenv("MORSI_CUDA_DEVICES", "2")
+    assert_same(M.apply("opening", e, one), y1, "2 devices, one plane in row bands, hrec60 opening")
