@@ -376,6 +376,7 @@ int morsi_dispatch(MorsiCtx *c, const int *e, const MorsiJob &job)
 		if (rc) return rc;
 		if (!handled) MORSI_CU(cudaMemsetAsync(flag, 0, sizeof(int), job.stream));
 		if (!handled) { rc = morsi_run_disk(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 2; }
+		if (!handled) { rc = morsi_run_runs(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 8; }
 		if (!handled) { rc = morsi_run_median3(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 4; }
 		if (!handled) { rc = morsi_run_median(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 4; }
 		if (!handled) { rc = morsi_run_line(c, de, job, flag, &handled); if (rc) return rc; if (handled) handled = 7; }
@@ -383,7 +384,7 @@ int morsi_dispatch(MorsiCtx *c, const int *e, const MorsiJob &job)
 		if (getenv("MORSI_CUDA_TRACE"))
 			fprintf(stderr, "morsi_cuda: op %d n=%d %dx%dx%d rows [%d,+%d): %s\n", job.op, de->n, job.w, job.h, job.planes,
 				job.y_row0, job.y_rows, handled == 1 ? "small" : handled == 2 ? "disk" :
-				handled == 4 ? "median" : handled == 5 ? "tiled" : handled == 6 ? "complete in one pass (3x3 with in-kernel signed zeros / tiled rank)" : handled == 7 ? "line (van Herk)" : "exact only");
+				handled == 4 ? "median" : handled == 5 ? "tiled" : handled == 6 ? "complete in one pass (3x3 with in-kernel signed zeros / tiled rank)" : handled == 7 ? "line (van Herk)" : handled == 8 ? "runs (runtime row-run shape)" : "exact only");
 		if (handled == 6) return MORSI_OK;             // exact as it stands: tiled rank, 3x3 with in-kernel signed zeros
 		if (handled)
 			return path == 2 ? MORSI_OK : run_exact_chunked(c, de, job, flag);

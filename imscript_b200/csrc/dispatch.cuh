@@ -83,6 +83,7 @@ int morsi_optin_smem(const void *kernel, int device, int bytes);
 // fast kernel families: set *handled = 1 when they took the job
 int morsi_run_small(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_disk(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
+int morsi_run_runs(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_median(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_median3(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);
 int morsi_run_tiled(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled);

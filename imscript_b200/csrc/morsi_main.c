@@ -185,28 +185,24 @@ static int try_stream_npy(const char *prog, int op, int *element, const char *in
 	unsigned hlen = hd[8] | (hd[9] << 8);
 	if (hlen >= sizeof dict || fread(dict, 1, hlen, f) != hlen) { fclose(f); return -1; }
 	dict[hlen] = 0;
-	long hh = 0, ww = 0;
+	long hh = 0, ww = 0, dd = 1;
 	const char *sh = strstr(dict, "'shape'");
-	if (!strstr(dict, "'<f4'") || !strstr(dict, "False") || !sh || sscanf(sh, "'shape': (%ld, %ld)", &hh, &ww) != 2
-			|| hh <= 0 || ww <= 0 || hh > 0x7fffffff || ww > 0x7fffffff) { fclose(f); return -1; }
-	/* exactly two dimensions: no second comma before the closing parenthesis */
+	if (!strstr(dict, "'<f4'") || !strstr(dict, "False") || !sh) { fclose(f); return -1; }
 	{
-		const char *p0 = strchr(sh, '('), *p1 = strchr(sh, ')');
+		/* (h, w) or (h, w, 1): one gray plane, rows contiguous */
+		const char *p0 = strchr(sh, '('), *p1 = p0 ? strchr(p0, ')') : NULL;
+		int nd = p0 && p1 ? sscanf(p0, "(%ld, %ld, %ld", &hh, &ww, &dd) : 0;
+		if (nd < 2 || (nd == 3 && dd != 1) || hh <= 0 || ww <= 0 || hh > 0x7fffffff || ww > 0x7fffffff) { fclose(f); return -1; }
 		int commas = 0;
-		for (const char *q = p0; q && p1 && q < p1; q++) commas += *q == ',';
-		if (commas != 1) { fclose(f); return -1; }
+		for (const char *q = p0; q < p1; q++) commas += *q == ',';
+		if (commas > 3) { fclose(f); return -1; }
 	}
 	FILE *g = fopen(out, "wb");
 	if (!g) { fclose(f); return -1; }
-	char oh[128];
-	int n = snprintf(oh, sizeof oh, "{'descr': '<f4', 'fortran_order': False, 'shape': (%ld, %ld), }", hh, ww);
-	int total = (10 + n + 1 + 63) / 64 * 64;            /* header padded to 64 bytes, newline last */
-	unsigned char ohd[10] = {0x93, 'N', 'U', 'M', 'P', 'Y', 1, 0, 0, 0};
-	ohd[8] = (total - 10) & 255; ohd[9] = (total - 10) >> 8;
-	fwrite(ohd, 1, 10, g);
-	fwrite(oh, 1, n, g);
-	for (int k = 10 + n; k < total - 1; k++) fputc(' ', g);
-	fputc('\n', g);
+	/* same type, same shape: the output header is the input's */
+	const int total = 10 + (int)hlen;
+	fwrite(hd, 1, 10, g);
+	fwrite(dict, 1, hlen, g);
 	struct npy_io io = {f, g, 10 + (long)hlen, total, (int)ww};
 	int rc = morsi_cuda_apply_stream(op, element, (int)ww, (int)hh, 1, npy_read_rows, npy_write_rows, &io);
 	fclose(f);

@@ -138,6 +138,40 @@ def test_median_fast_kernels(quad, monkeypatch):
             assert_same(M.apply("median", e, x), o.apply("median", e, x), f"{name} median {w}x{h} quad={quad}")
 
 
+def test_runtime_rowrun_shapes():
+    """k_runs: row-run elements whose shape is only known at run time -- disks outside the compiled table
+    (disk6.5, disk16 ... disk32), rectangles given as user lists, medium hrec -- on aligned and odd widths,
+    several strips / bands, NaN / Inf / +-0 in plane 1, and as row bands"""
+    o = oracle()
+    rect = np.array([35, 0, 0, 0] + [v for dx in range(-3, 4) for dy in range(-2, 3) for v in (dx, dy)], dtype=np.int32)   # 7x5
+    cases = [("disk6.5", 203, 150), ("disk16", 260, 140), ("disk20", 300, 101), ("disk25.3", 131, 120),
+             ("disk32", 120, 90), ("hrec13", 333, 40), ("hrec31", 512, 33), (rect, 97, 131), ("disk16", 1100, 300)]
+    for name, w, h in cases:
+        e = o.element(name) if isinstance(name, str) else name
+        assert M.describe_element(e).startswith("rowrun"), name
+        x = np.stack([M.synth_host(w, h, plane=p, seed=91, dist=2 if p == 1 else 0) for p in range(2)])
+        x[0][x[0] == 0] = 0.0
+        big = e[0] > 1500
+        ops = ["erosion", "dilation", "opening", "tophat"] if big else \
+            ["erosion", "dilation", "opening", "closing", "tophat", "bothat", "gradient", "igradient", "laplacian",
+             "oscillation", "cblur", "eblur"]
+        if w * h > 100000:
+            ops = ["closing", "gradient"]
+        for op in ops:
+            assert_same(M.apply(op, e, x), o.apply(op, e, x), f"runs {name if isinstance(name, str) else 'rect7x5'} {op} {w}x{h}")
+    # row bands through the band entry point
+    e = o.element("disk16")
+    x = M.synth_host(260, 200, seed=92, dist=2)
+    want = o.apply("tophat", e, x)
+    up, down = M.halo_rows("tophat", e)
+    for b0, b1 in [(0, 70), (70, 71), (71, 200)]:
+        i0, i1 = max(0, b0 - up), min(200, b1 + down)
+        bx = M.DeviceBuffer.from_host(np.ascontiguousarray(x[i0:i1]))
+        by = M.DeviceBuffer((b1 - b0) * 260 * 4)
+        M.apply_band_device("tophat", e, bx, i0, i1 - i0, by, b0, b1 - b0, 260, 200)
+        assert_same(by.to_host((b1 - b0, 260)), want[b0:b1], f"runs band [{b0},{b1})")
+
+
 def test_long_lines_van_herk():
     """hrec / vrec long enough for the van Herk / Gil-Werman kernels (k_line.cuh), also as a
     user list with an off-centre line, on ragged sizes with NaN / Inf / +-0 sprinkled in"""
