@@ -348,6 +348,34 @@ def pcie_ceiling(env, hx, hy, nbytes):
     return env.world * nb / sec / 1e9
 
 
+def measure_cli(name, hx_array_fn):
+    """Wall time of the drop-in command line itself on this workload's image (the path a user of the
+    reference runs): `morsi ELEMENT OP in.npy out.npy`, malloc'd iio buffers, process start-up and
+    CUDA context creation included.  Returns None when the CLI or a scratch directory is missing."""
+    import shutil
+    import tempfile
+    element, ops, w, h, planes, seed, desc = WORKLOADS[name]
+    cli = os.path.join(ROOT, "imscript_b200", "lib", "morsi")
+    if not os.path.exists(cli) or w * h * planes * 4 > (1 << 30):
+        return None
+    tmp = tempfile.mkdtemp(prefix="morsi_bench_")
+    try:
+        fin, fout = os.path.join(tmp, "in.npy"), os.path.join(tmp, "out.npy")
+        np.save(fin, hx_array_fn())                       # (h, w, planes): iio's pixel-interleaved NPY
+        t0 = time.perf_counter()
+        for op in ops:
+            r = subprocess.run([cli, element, op, fin, fout], capture_output=True)
+            if r.returncode != 0:
+                return {"error": r.stderr.decode()[-200:]}
+        dt = time.perf_counter() - t0
+        nbytes = os.path.getsize(fin)
+        return {"value": w * h * planes * len(ops) / dt / 1e6, "unit": "Mpixel/s", "seconds": dt,
+                "file_bytes_in": nbytes, "what": "`morsi %s OP in.npy out.npy` for OP in %s: process start, iio read, "
+                "upload / kernels / download, iio write (page cache, no disk)" % (element, ops)}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def measure_planes(env, name):
     """plane / frame workloads: every rank its own planes, no data-path collective"""
     M, L, check, ct = env.M, env.L, env.check, env.ct
@@ -390,6 +418,11 @@ def measure_planes(env, name):
                        "pcie_gbs_per_direction_all_ranks": ceil_gbs,
                        "how": "every rank copying 1 GiB pinned H2D and D2H at once; 4 B up + 4 B down per sample"}}
     e2e["frac_of_ceiling"] = e2e["value"] / e2e["ceiling"]["value"]
+    if env.rank == 0 and env.world == 1 and not args.no_cpu:
+        def as_vec():
+            a = np.ctypeslib.as_array(ct.cast(hx, ct.POINTER(ct.c_float)), shape=(planes, h, w))
+            return np.ascontiguousarray(np.moveaxis(a, 0, -1))
+        e2e["cli"] = measure_cli(name, as_vec)
     L.morsi_cuda_host_free(hx)
     L.morsi_cuda_host_free(hy)
     return {"ms_per_step": ms_per_step, "launches": launches, "clocks": clocks, "e2e": e2e,

@@ -95,6 +95,7 @@ struct TiledLaunch {
 	size_t smem;
 	const LineGeom *line = nullptr;   // non-NULL: the van Herk line kernels (k_line.cuh) instead
 	size_t line_smem = 0;
+	int exact = 0;                    // 1: the order-preserving form of k_tiled_minmax (the gated re-run)
 };
 
 template <int EPI>
@@ -121,7 +122,24 @@ static int launch_tiled_t(const ExactArgs &a, const TiledLaunch &t, int planes, 
 		MORSI_CU(cudaGetLastError());
 		return MORSI_OK;
 	}
-	if ((rc = morsi_optin_smem((const void *)k_tiled_minmax<EPI>, device, 200 * 1024))) return rc;
+	if (t.exact) {
+		if ((rc = morsi_optin_smem((const void *)k_tiled_minmax<EPI, true>, device, 200 * 1024))) return rc;
+		// one launch, tile rows walked inside the kernel; a gated launch (a no-op nearly always) stays small
+		const int rows_y = (a.y_rows + TILED_TY - 1) / TILED_TY;
+		const unsigned gx = (unsigned)((a.w + TILED_TX - 1) / TILED_TX);
+		unsigned gy = (unsigned)(rows_y < 65535 ? rows_y : 65535);
+		if (a.gate) {
+			const unsigned long long per_row = (unsigned long long)gx * (unsigned)planes;
+			unsigned want = (unsigned)(148ull * 4 / (per_row ? per_row : 1));
+			if (want < 1) want = 1;
+			if (gy > want) gy = want;
+		}
+		k_tiled_minmax<EPI, true><<<dim3(gx, gy, planes), dim3(32, 8), t.smem, s>>>(a, t.g, t.flag);
+		morsi_count_launch(1);
+		MORSI_CU(cudaGetLastError());
+		return MORSI_OK;
+	}
+	if ((rc = morsi_optin_smem((const void *)k_tiled_minmax<EPI, false>, device, 200 * 1024))) return rc;
 	const int rows_y = (a.y_rows + TILED_TY - 1) / TILED_TY;
 	for (int r0 = 0; r0 < rows_y; r0 += 65535) {   // gridDim.y limit
 		ExactArgs sub = a;
@@ -131,7 +149,7 @@ static int launch_tiled_t(const ExactArgs &a, const TiledLaunch &t, int planes, 
 		sub.y = a.y + (long long)r0 * TILED_TY * a.w;
 		if (a.y2) sub.y2 = a.y2 + (long long)r0 * TILED_TY * a.w;
 		dim3 grid((a.w + TILED_TX - 1) / TILED_TX, nb, planes);
-		k_tiled_minmax<EPI><<<grid, dim3(32, 8), t.smem, s>>>(sub, t.g, t.flag);
+		k_tiled_minmax<EPI, false><<<grid, dim3(32, 8), t.smem, s>>>(sub, t.g, t.flag);
 		morsi_count_launch(1);
 	}
 	MORSI_CU(cudaGetLastError());
@@ -314,25 +332,32 @@ int morsi_run_line(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *
 	return MORSI_OK;
 }
 
+// the tile geometry of an element for k_tiled_*; false when a tile does not fit shared memory
+static bool tiled_setup(const DevElement *de, const OpPlan &plan, int *flag, TiledLaunch *t)
+{
+	if (de->n < 1 || de->n > 8192 || !de->d_tile_offs) return false;
+	t->g.xmin = de->info.xmin; t->g.xmax = de->info.xmax; t->g.ymin = de->info.ymin; t->g.ymax = de->info.ymax;
+	t->g.pw = TILED_TX + de->info.xmax - de->info.xmin;
+	t->g.ph = TILED_TY + de->info.ymax - de->info.ymin;
+	t->g.tile_offs = de->d_tile_offs;
+	t->g.two_tiles = 0;
+	t->flag = flag;
+	t->smem = (size_t)t->g.pw * t->g.ph * sizeof(float) + (size_t)de->n * sizeof(int);
+	// oscillation's last pass needs two tiles
+	const size_t worst = t->smem + ((plan.t_min && plan.t_max) ? (size_t)t->g.pw * t->g.ph * sizeof(float) : 0);
+	return worst <= 200 * 1024;
+}
+
 // Arbitrary lists the specialised families left: evaluate from shared-memory tiles.
 int morsi_run_tiled(MorsiCtx *c, const DevElement *de, const MorsiJob &job, int *flag, int *handled)
 {
 	*handled = 0;
 	const OpPlan plan = morsi_op_plan(job.op);
-	if (plan.special == 1 || de->n < 1 || de->n > 8192 || !de->d_tile_offs) return MORSI_OK;
+	if (plan.special == 1) return MORSI_OK;
 	static const bool off = getenv("MORSI_TILED") && !strcmp(getenv("MORSI_TILED"), "0");
 	if (off) return MORSI_OK;
 	TiledLaunch t;
-	t.g.xmin = de->info.xmin; t.g.xmax = de->info.xmax; t.g.ymin = de->info.ymin; t.g.ymax = de->info.ymax;
-	t.g.pw = TILED_TX + de->info.xmax - de->info.xmin;
-	t.g.ph = TILED_TY + de->info.ymax - de->info.ymin;
-	t.g.tile_offs = de->d_tile_offs;
-	t.g.two_tiles = 0;
-	t.flag = flag;
-	t.smem = (size_t)t.g.pw * t.g.ph * sizeof(float) + (size_t)de->n * sizeof(int);
-	// oscillation's last pass needs two tiles
-	const size_t worst = t.smem + ((plan.t_min && plan.t_max) ? (size_t)t.g.pw * t.g.ph * sizeof(float) : 0);
-	if (worst > 200 * 1024) return MORSI_OK;
+	if (!tiled_setup(de, plan, flag, &t)) return MORSI_OK;
 	if (plan.special == 2) {
 		// rank: one pass, no temporaries, exact in any order (no gated re-run needed)
 		int rc = morsi_optin_smem((const void *)k_tiled_rank, c->device, 200 * 1024);
@@ -386,8 +411,19 @@ int morsi_dispatch(MorsiCtx *c, const int *e, const MorsiJob &job)
 				job.y_row0, job.y_rows, handled == 1 ? "small" : handled == 2 ? "disk" :
 				handled == 4 ? "median" : handled == 5 ? "tiled" : handled == 6 ? "complete in one pass (3x3 with in-kernel signed zeros / tiled rank)" : handled == 7 ? "line (van Herk)" : handled == 8 ? "runs (runtime row-run shape)" : "exact only");
 		if (handled == 6) return MORSI_OK;             // exact as it stands: tiled rank, 3x3 with in-kernel signed zeros
-		if (handled)
-			return path == 2 ? MORSI_OK : run_exact_chunked(c, de, job, flag);
+		if (handled) {
+			if (path == 2) return MORSI_OK;
+			// the order-preserving re-run, gated on the flag: from shared-memory tiles where the
+			// element fits one (every min / max operation), else straight from global memory
+			const OpPlan plan = morsi_op_plan(job.op);
+			TiledLaunch te;
+			static const bool no_te = getenv("MORSI_TILED_EXACT") && !strcmp(getenv("MORSI_TILED_EXACT"), "0");
+			if (!plan.special && !no_te && tiled_setup(de, plan, flag, &te)) {
+				te.exact = 1;
+				return run_exact_chunked(c, de, job, flag, &te);
+			}
+			return run_exact_chunked(c, de, job, flag);
+		}
 	}
 	return run_exact_chunked(c, de, job, nullptr);
 }

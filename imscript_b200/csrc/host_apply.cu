@@ -124,6 +124,25 @@ extern "C" int morsi_cuda_apply(int op, const int *e, const float *x, float *y,
 					per_dev[d].push_back({p, r, std::min(b1, r + band)});
 			}
 	}
+	// Pipeline ramp: the first upload and the last download of a call overlap nothing, so the
+	// first and the last chunk of every device are cut short (a quarter, then the rest).
+	for (auto &list : per_dev) {
+		const int min_rows = std::max(32, 4 * (up + down));
+		if (list.size() >= 2) {
+			Chunk f = list.front();
+			const int q = (f.r1 - f.r0) / 4;
+			if (q >= min_rows) {
+				list.front().r0 = f.r0 + q;
+				list.insert(list.begin(), Chunk{f.plane, f.r0, f.r0 + q});
+			}
+			Chunk l = list.back();
+			const int ql = (l.r1 - l.r0) / 4;
+			if (ql >= min_rows) {
+				list.back().r1 = l.r1 - ql;
+				list.push_back(Chunk{l.plane, l.r1 - ql, l.r1});
+			}
+		}
+	}
 	if (ndev == 1) {
 		MorsiCtx *c; rc = morsi_ctx_current(&c); if (rc) return rc;
 		return run_chunks(c->device, op, e, x, y, w, h, per_dev[0], up, down);

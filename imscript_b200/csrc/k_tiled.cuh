@@ -46,15 +46,24 @@ __device__ __forceinline__ void tiled_load(float *tile, const Band &src, int pla
 	}
 }
 
-template <int EPI>
+// EXACT: the order-preserving form -- `v <= a ? v : a` in element order, exactly glibc's
+// fmin / fmax on ties -- at two instructions per compare instead of one.
+// It is the re-run the dispatcher gates on the "saw a -0.0" word (p.gate) of the fast
+// families: the same results as k_exact_minmax, from shared-memory tiles instead of
+// bounds-checked global gathers.  Tile rows are walked with the stride of gridDim.y, so a
+// gated launch can be a small grid that costs a few microseconds when it is a no-op.
+template <int EPI, bool EXACT>
 __global__ void __launch_bounds__(256) k_tiled_minmax(ExactArgs p, TiledGeom g, int *flag)
 {
+	if (p.gate && *p.gate == 0) return;
 	extern __shared__ float tiled_smem[];
 	constexpr bool NA = EpiNeeds<EPI>::a, NB = EpiNeeds<EPI>::b;
 	const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
 	const int plane = blockIdx.z;
-	const int bx = blockIdx.x * TILED_TX, by = blockIdx.y * TILED_TY;   // tile origin, rows relative to y_row0
 	const int pw = g.pw, ph = g.ph;
+	const int bx = blockIdx.x * TILED_TX;
+	for (int by = blockIdx.y * TILED_TY; by < p.y_rows; by += gridDim.y * TILED_TY) {   // tile origin, rows relative to y_row0
+	__syncthreads();                                                      // the previous tile has been consumed
 	float *tile_a = tiled_smem;                                  // erosion-side source (or the shared one)
 	float *tile_b = g.two_tiles ? tiled_smem + pw * ph : tiled_smem;
 	int *offs = reinterpret_cast<int *>(tiled_smem + (g.two_tiles ? 2 : 1) * pw * ph);
@@ -65,7 +74,7 @@ __global__ void __launch_bounds__(256) k_tiled_minmax(ExactArgs p, TiledGeom g, 
 	if (NA || !g.two_tiles) tiled_load(tile_a, NA ? p.a_src : p.b_src, plane, p.w, p.h, gx0, gy0, pw, ph, tid, negzero, need_lo, need_hi);
 	if (NB && g.two_tiles) tiled_load(tile_b, p.b_src, plane, p.w, p.h, gx0, gy0, pw, ph, tid, negzero, need_lo, need_hi);
 	for (int k = tid; k < p.n; k += 256) offs[k] = g.tile_offs[k];
-	if (__syncthreads_or(negzero) && tid == 0) atomicOr(flag, 1);
+	if (__syncthreads_or(negzero) && tid == 0 && !EXACT) atomicOr(flag, 1);
 
 	float a[2][4], b[2][4];
 #pragma unroll
@@ -81,10 +90,13 @@ __global__ void __launch_bounds__(256) k_tiled_minmax(ExactArgs p, TiledGeom g, 
 		for (int r = 0; r < 2; r++)
 #pragma unroll
 			for (int c = 0; c < 4; c++) {
-				if (NA) { const float v = qa[o + r * row8 + 32 * c]; a[r][c] = fminf(a[r][c], v); }
+				if (NA) {
+					const float v = qa[o + r * row8 + 32 * c];
+					a[r][c] = EXACT ? ((v <= a[r][c]) ? v : a[r][c]) : fminf(a[r][c], v);
+				}
 				if (NB) {
 					const float v = (NA && !g.two_tiles) ? qa[o + r * row8 + 32 * c] : qb[o + r * row8 + 32 * c];
-					b[r][c] = fmaxf(b[r][c], v);
+					b[r][c] = EXACT ? ((v >= b[r][c]) ? v : b[r][c]) : fmaxf(b[r][c], v);
 				}
 			}
 	}
@@ -104,6 +116,7 @@ __global__ void __launch_bounds__(256) k_tiled_minmax(ExactArgs p, TiledGeom g, 
 			else p.y[o] = epilogue<EPI>(a[r][c], b[r][c], x);
 		}
 	}
+	}   // tile rows
 }
 
 // ---- rank (src/morsi.c:122-139) from the same tiles ------------------------------------
