@@ -221,7 +221,19 @@ struct DiskCfg {
 #ifndef DISK_RING_BYTES
 #define DISK_RING_BYTES (20 * 1024)
 #endif
-	static constexpr int NG = DISK_RING_BYTES / (GROUP * 4) < 2 ? 2 : (DISK_RING_BYTES / (GROUP * 4) > 8 ? 8 : DISK_RING_BYTES / (GROUP * 4));
+	// the 255-register shapes run one CTA per SM: shared memory is plentiful there, and a deeper
+	// ring gives the two stages (which otherwise meet at every group boundary) room to drift
+#ifndef DISK_RING_BYTES_BIG
+#define DISK_RING_BYTES_BIG (20 * 1024)
+#endif
+	// measured on B200 (profiles/r2_kdisk_ring_variants.txt): three groups help the single-stage kernel
+	// (disk7 erosion of 4096x4096x3: 0.085 -> 0.079 ms = 5.1 TB/s, still three CTAs per SM); the fused
+	// two-stage kernel loses with them (one CTA per SM less: 0.149 -> 0.174 ms), and so do the big disks
+#ifndef DISK_RING_BYTES_SINGLE
+#define DISK_RING_BYTES_SINGLE (54 * 1024)
+#endif
+	static constexpr int RING_BYTES = (C * (2 * R + 2) > 64) ? DISK_RING_BYTES_BIG : (TWO ? DISK_RING_BYTES : DISK_RING_BYTES_SINGLE);
+	static constexpr int NG = RING_BYTES / (GROUP * 4) < 2 ? 2 : (RING_BYTES / (GROUP * 4) > 8 ? 8 : RING_BYTES / (GROUP * 4));
 	static constexpr unsigned GROUP_BYTES = GROUP * 4u;
 	static constexpr int NACC = 2 * R + 2;            // accumulator slots per column
 	static constexpr int THREADS = TWO ? 2 * NT : NT;
@@ -647,7 +659,7 @@ template <class S, int C, int W>
 struct DiskCfgBoth {
 	using K1 = DiskCfg<S, C, W, false>;
 	static constexpr int R = K1::R, LH = K1::LH, NT = K1::NT, TW = K1::TW, OUTW = K1::OUTW, RP = K1::RP;
-	static constexpr int PERIOD = K1::PERIOD, GP = K1::GP, PAIR = K1::PAIR, GROUP = K1::GROUP, NG = K1::NG;
+	static constexpr int PERIOD = K1::PERIOD, GP = K1::GP, PAIR = K1::PAIR, GROUP = K1::GROUP, NG = 2;
 	static constexpr unsigned GROUP_BYTES = K1::GROUP_BYTES;
 	static constexpr int APAIR = 2 * TW;              // role A's rows: just the strip's own columns
 	static constexpr int AGROUP = GP * APAIR;
