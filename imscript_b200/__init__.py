@@ -6,7 +6,7 @@ imscript_b200/lib/libmorsi_cuda.so plus the `morsi` host program.  There is no
 CPU fallback: importing works without a GPU (so that the build can be checked),
 every compute call raises MorsiError without one.
 """
-from .binding import (OPS, MorsiError, DeviceBuffer, apply, apply_device, apply_band_device, apply_sharded, apply_interleaved, apply_stream,  # noqa: F401
+from .binding import (OPS, MorsiError, DeviceBuffer, apply, apply_device, apply_band_device, apply_sharded, apply_interleaved, apply_stream, apply_chain,  # noqa: F401
                       build_element, describe_element, device_count, halo_rows, lib, lib_path,
                       parse_element, parse_operation, synth_host, EXPORTED_SYMBOLS)
 from . import morsi  # noqa: F401

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "morsi_cuda_event_elapsed_ms", "morsi_cuda_event_destroy",
     "morsi_shard_create", "morsi_shard_handle", "morsi_shard_connect", "morsi_shard_rows",
     "morsi_shard_buffer", "morsi_shard_stream", "morsi_shard_apply", "morsi_shard_apply_host",
-    "morsi_cuda_apply_all_device", "morsi_cuda_apply_interleaved", "morsi_cuda_apply_stream",
+    "morsi_cuda_apply_all_device", "morsi_cuda_apply_interleaved", "morsi_cuda_apply_stream", "morsi_cuda_apply_chain",
     "morsi_shard_exchange", "morsi_cuda_stream_create", "morsi_cuda_stream_destroy",
     "morsi_shard_sync", "morsi_shard_halo_bytes", "morsi_shard_destroy", "morsi_cuda_apply_sharded",
 ]
@@ -296,6 +296,33 @@ def apply_stream(op, e, w, h, planes, read_rows, write_rows):
             return 1
     check(lib().morsi_cuda_apply_stream(_op(op), e.ctypes.data_as(_i32p), w, h, planes,
                                         READ_ROWS_FN(rd), WRITE_ROWS_FN(wr), None))
+
+
+class Quantizer(ctypes.Structure):
+    _fields_ = [("black", ctypes.c_float), ("white", ctypes.c_float), ("to_uint8", ctypes.c_int)]
+
+
+def apply_chain(steps, x, quant=None):
+    """steps: [(op, element), ...] applied in order on the device; quant: None or (black, white, to_uint8)
+    = qeasy (src/qeasy.c) as the last stage.  x: (h,w) or (planes,h,w) float32 -> same shape, float32 or uint8."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    h, w = x.shape[-2:]
+    planes = int(np.prod(x.shape[:-2])) if x.ndim > 2 else 1
+    es = [_e(e) for _, e in steps]
+    ops = (ctypes.c_int * len(steps))(*[_op(o) for o, _ in steps])
+    eps = (_i32p * len(steps))(*[e.ctypes.data_as(_i32p) for e in es])
+    q = None
+    y = np.empty_like(x)
+    if quant is not None:
+        q = Quantizer(float(quant[0]), float(quant[1]), int(bool(quant[2])))
+        if quant[2]:
+            y = np.empty(x.shape, np.uint8)
+    L = lib()
+    L.morsi_cuda_apply_chain.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_i32p), _vp, _vp,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(Quantizer)]
+    check(L.morsi_cuda_apply_chain(len(steps), ops, eps, x.ctypes.data, y.ctypes.data, w, h, planes,
+                                   ctypes.byref(q) if q is not None else None))
+    return y
 
 
 def apply_sharded(op, e, x, ndev, iterations=1):

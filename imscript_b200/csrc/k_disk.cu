@@ -879,6 +879,156 @@ k_disk_both(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 	if (__syncthreads_or(zmin == INT_MIN) && tid == 0) atomicOr(p.flag, 1);
 }
 
+// ---- the same, with both reductions in EVERY thread (small disks) -------------------------
+// For R <= 6 a thread can hold the accumulators of the minimum AND of the maximum
+// (2 x C x (2R+2) registers): one role, one ring, no hand-off between warps -- the two
+// marches read the same shared-memory rows and are independent instruction streams that
+// fill each other's latency.  Epilogue and store as in k_disk_both.
+template <class S, int C, int W>
+struct DiskCfgDual {
+	using K1 = DiskCfg<S, C, W, false>;
+	static constexpr int R = K1::R, LH = K1::LH, NT = K1::NT, TW = K1::TW, OUTW = K1::OUTW, RP = K1::RP;
+	static constexpr int PERIOD = K1::PERIOD, GP = K1::GP, PAIR = K1::PAIR, GROUP = K1::GROUP, NG = 2;
+	static constexpr unsigned GROUP_BYTES = K1::GROUP_BYTES;
+	static constexpr int NACC = K1::NACC;
+	static constexpr int THREADS = NT;
+	static constexpr size_t SMEM = (size_t)NG * GROUP * sizeof(float) + 2 * NG * sizeof(unsigned long long) + 128;
+	static constexpr int MINB = 65536 / (255 * THREADS) > 0 ? 65536 / (255 * THREADS) : 1;
+	static constexpr bool OK = 2 * C * (2 * R + 2) <= 112;     // the accumulators of both flavours fit the register file
+};
+
+template <class S, int C, int W>
+__global__ void __launch_bounds__(DiskCfgDual<S, C, W>::THREADS, DiskCfgDual<S, C, W>::MINB)
+k_disk_dual(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
+{
+	using K = DiskCfgDual<S, C, W>;
+	using Dmin = DiskMarch<S, C, K::LH, false>;
+	using Dmax = DiskMarch<S, C, K::LH, true>;
+	constexpr int R = K::R, LH = K::LH, RP = K::RP, PERIOD = K::PERIOD, GP = K::GP, NG = K::NG;
+	constexpr int PAIR = K::PAIR, GROUP = K::GROUP;
+	extern __shared__ unsigned char smem_raw[];
+	float *ring = reinterpret_cast<float *>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+	const unsigned bars = smem_u32(ring + (size_t)NG * GROUP);
+	const unsigned full_in = bars, empty_in = bars + 8 * NG;
+
+	const int tid = threadIdx.x;
+	const int lane = tid & 31;
+	const int plane = blockIdx.z;
+	const int cx0 = blockIdx.x * K::OUTW;
+	const int o_base = blockIdx.y * p.band_rows;
+	const int nout = min(p.band_rows, p.y_rows - o_base);
+	const int Y0 = p.y_row0 + o_base;
+	const int w = p.w;
+	const long long pitch = p.pitch;
+	const int G2 = (nout + 2 * R + 1) / 2;
+	const int in_row0 = Y0 - R;
+	const int gc0 = cx0 - LH;
+	const int gxb = (gc0 >= 0 ? gc0 : gc0 - bw + 1) / bw;
+	const int shift = gc0 - gxb * bw;
+
+	if (tid == 0) {
+		for (int i = 0; i < NG; i++) { mbar_init(full_in + 8 * i, 1); mbar_init(empty_in + 8 * i, W); }
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("prefetch.tensormap [%0];" :: "l"(&tm) : "memory");
+	}
+	__syncthreads();
+
+	const unsigned ring_u32 = smem_u32(ring);
+	const int trow0 = in_row0 - p.src.row0;
+	const int ngroups = (G2 + GP - 1) / GP;
+	auto load_group = [&](int gl) {
+		const int slot = gl % NG;
+		if (gl >= NG) mbar_wait(empty_in + 8 * slot, ((gl / NG) - 1) & 1);
+		mbar_arrive_tx(full_in + 8 * slot, K::GROUP_BYTES);
+		tma_load_4d(ring_u32 + slot * K::GROUP_BYTES, &tm, 0, gxb, trow0 + 2 * GP * gl, plane, full_in + 8 * slot);
+	};
+	if (tid == 0) {
+		for (int gl = 0; gl < NG - 1 && gl < ngroups; gl++) load_group(gl);
+	}
+
+	float accA[C][K::NACC], hsA[C][4], accB[C][K::NACC], hsB[C][4];
+#pragma unroll
+	for (int c = 0; c < C; c++) {
+#pragma unroll
+		for (int k = 0; k < K::NACC; k++) { accA[c][k] = Dmin::init(); accB[c][k] = Dmax::init(); }
+#pragma unroll
+		for (int k = 0; k < 4; k++) { hsA[c][k] = Dmin::init(); hsB[c][k] = Dmax::init(); }
+	}
+	int zmin = 0, zdummy = 0;
+	const float *my_ring = ring + shift + C * tid;
+	const bool lane0 = lane == 0;
+	const int x = cx0 + C * tid;
+	const bool col_ok = x < w;
+	const bool pad_edge = col_ok && x + C > w;
+	float *yq = p.y + plane * p.y_pstride + (long long)(Y0 - p.y_row0 - 2 * R) * pitch + x;
+	const float *xq = p.xop.p ? p.xop.p + plane * p.xop.pstride + (long long)(Y0 - p.xop.row0 - 2 * R) * pitch + x : nullptr;
+	const int epi = p.epi;
+	int gi = 0;
+	const float *grp = my_ring;
+	unsigned grp_empty = empty_in;
+
+#pragma unroll 1
+	for (int g0 = 0; g0 < G2; g0 += PERIOD) {
+#pragma unroll
+		for (int s = 0; s < PERIOD; s++) {
+			const int g = g0 + s;
+			if (g < G2) {
+				const int pos = s % GP;
+				if (pos == 0) {
+					const int slot = gi % NG;
+					if (tid == 0 && gi + NG - 1 < ngroups) load_group(gi + NG - 1);
+					mbar_wait_warp(full_in + 8 * slot, (gi / NG) & 1);
+					grp = my_ring + slot * GROUP;
+					grp_empty = empty_in + 8 * slot;
+					gi++;
+				}
+				const float *rowA = grp + pos * PAIR;
+				const int o0 = 2 * g - 2 * R;
+				const bool e0 = col_ok && (unsigned)o0 < (unsigned)nout;
+				const bool e1 = col_ok && (unsigned)(o0 + 1) < (unsigned)nout;
+				float xv0[C], xv1[C], a0[C], a1[C];
+#pragma unroll
+				for (int c = 0; c < C; c++) { xv0[c] = 0.f; xv1[c] = 0.f; }
+				if (e0 && xq) load_cols<C>(xq, xv0);
+				if (e1 && xq) load_cols<C>(xq + pitch, xv1);
+				Dmin::step(accA, hsA, s % (R + 1), rowA, rowA + RP, zmin, true,
+					[]() {},
+					[&](const float (&m0)[C], const float (&m1)[C]) {
+#pragma unroll
+						for (int c = 0; c < C; c++) { a0[c] = m0[c]; a1[c] = m1[c]; }
+					});
+				Dmax::step(accB, hsB, s % (R + 1), rowA, rowA + RP, zdummy, false,
+					[&]() { if (pos == GP - 1 && lane0) mbar_arrive(grp_empty); },
+					[&](const float (&m0)[C], const float (&m1)[C]) {
+					if (e0) {
+						const float4 r = disk_epi4<true>(epi, m0[0], m0[1], C == 4 ? m0[2] : 0.f, C == 4 ? m0[3] : 0.f,
+								a0[0], a0[1], C == 4 ? a0[2] : 0.f, C == 4 ? a0[3] : 0.f,
+								xv0[0], xv0[1], C == 4 ? xv0[2] : 0.f, C == 4 ? xv0[3] : 0.f);
+						if (C == 4) *(float4 *)yq = r; else *(float2 *)yq = make_float2(r.x, r.y);
+					}
+					if (e1) {
+						const float4 r = disk_epi4<true>(epi, m1[0], m1[1], C == 4 ? m1[2] : 0.f, C == 4 ? m1[3] : 0.f,
+								a1[0], a1[1], C == 4 ? a1[2] : 0.f, C == 4 ? a1[3] : 0.f,
+								xv1[0], xv1[1], C == 4 ? xv1[2] : 0.f, C == 4 ? xv1[3] : 0.f);
+						if (C == 4) *(float4 *)(yq + pitch) = r; else *(float2 *)(yq + pitch) = make_float2(r.x, r.y);
+					}
+					if (pad_edge) {
+#pragma unroll
+						for (int c = 0; c < C; c++)
+							if (x + c >= w) {
+								if (e0) yq[c] = CUDART_NAN_F;
+								if (e1) yq[pitch + c] = CUDART_NAN_F;
+							}
+					}
+				});
+				yq += 2 * pitch;
+				if (xq) xq += 2 * pitch;
+			}
+		}
+	}
+	if (__syncthreads_or(zmin == INT_MIN) && tid == 0) atomicOr(p.flag, 1);
+}
+
 // ---- host side --------------------------------------------------------------------
 // Bands: every CTA marches `rows` output rows plus a warm-up of 2*reach rows
 // per stage, and CTAs run in waves of `slots`; pick the band count that
@@ -1034,6 +1184,32 @@ static int disk_launch_both(const MorsiCtx *c, const DiskArgs &a0, int planes, c
 	return MORSI_OK;
 }
 
+template <class S, int C, int W>
+static int disk_launch_dual(const MorsiCtx *c, const DiskArgs &a0, int planes, cudaStream_t st)
+{
+	using K = DiskCfgDual<S, C, W>;
+	DiskArgs a = a0;
+	static int occs[64];
+	int &occ = occs[c->device & 63];
+	if (occ <= 0) {
+		cudaFuncSetAttribute(k_disk_dual<S, C, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+		int o = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_disk_dual<S, C, W>, K::THREADS, K::SMEM) != cudaSuccess || o < 1) o = 1;
+		occ = o;
+	}
+	const int strips = (a.w + K::OUTW - 1) / K::OUTW;
+	a.band_rows = pick_band_rows((long long)c->sm_count * occ, a.y_rows, (long long)strips * planes, S::R, 1, nullptr);
+	CUtensorMap tm;
+	int bw = 4;
+	int rc = disk_tensor_map(&tm, a.src, a.src_rows, a.pitch, planes, K::RP, 2 * K::GP, &bw);
+	if (rc) return rc;
+	dim3 grid(strips, (a.y_rows + a.band_rows - 1) / a.band_rows, planes);
+	k_disk_dual<S, C, W><<<grid, K::THREADS, K::SMEM, st>>>(tm, a, bw);
+	morsi_count_launch(1);
+	MORSI_CU(cudaGetLastError());
+	return MORSI_OK;
+}
+
 static int disk_forced_w()
 {
 	const char *s = getenv("MORSI_DISK_W");            // 2 or 4 warps per stage; default: planned
@@ -1061,6 +1237,11 @@ static int disk_shape_c(MorsiCtx *c, const DiskArgs &a, int planes, bool ismax, 
 {
 	using S = Shape<ID>;
 	if (a.both) {
+		// both reductions in every thread where the register file holds them (R <= 6; MORSI_DISK_DUAL=0: the two-role kernel)
+		static const bool no_dual = getenv("MORSI_DISK_DUAL") && !strcmp(getenv("MORSI_DISK_DUAL"), "0");
+		if (DiskCfgDual<S, C, 2>::OK && !no_dual) {
+			if constexpr (DiskCfgDual<S, C, 2>::OK) return disk_launch_dual<S, C, 2>(c, a, planes, st);
+		}
 		// 2 warps per role for the small disks, 4 for the ones that need every register
 		if (disk_forced_w() == 4 || (disk_forced_w() != 2 && DiskCfgBoth<S, C, 2>::REGS >= 255))
 			return disk_launch_both<S, C, 4>(c, a, planes, st);

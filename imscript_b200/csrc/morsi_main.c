@@ -214,6 +214,7 @@ static int try_stream_npy(const char *prog, int op, int *element, const char *in
 /* the iio "vec" entry points (src/iio.h:33,176): pixel-interleaved samples */
 float *iio_read_image_float_vec(const char *fname, int *w, int *h, int *pd);
 void iio_write_image_float_vec(char *fname, float *x, int w, int h, int pd);
+void iio_write_image_uint8_split(char *fname, unsigned char *x, int w, int h, int pd);
 
 int main_morsi(int c, char **v)
 {
@@ -240,6 +241,26 @@ int main_morsi(int c, char **v)
 	}
 	if (try_stream_npy(*v, op, element, filename_in, filename_out) == 0)
 		return 0;
+
+	/* extension 3: MORSI_CUDA_QEASY="black white" = `morsi E OP in | qeasy black white - out`
+	 * (doc/tutorial/i.html:221-225, src/qeasy.c): the quantiser runs on the device as the last
+	 * kernel of the chain and the 8-bit result comes back as bytes. */
+	const char *qe = getenv("MORSI_CUDA_QEASY");
+	float black, white;
+	if (qe && sscanf(qe, "%f %f", &black, &white) == 2) {
+		int w, h, pd;
+		float *x = iio_read_image_float_split(filename_in, &w, &h, &pd);
+		unsigned char *y8 = malloc((size_t)w * h * pd);
+		if (!y8) { fprintf(stderr, "FAIL(\"%s\"): out of memory\n", *v); exit(-1); }
+		morsi_quantizer q = {black, white, 1};
+		const int *els[1] = {element};
+		int rc = morsi_cuda_apply_chain(1, &op, els, x, y8, w, h, pd, &q);
+		if (rc != MORSI_OK) die(*v, rc);
+		iio_write_image_uint8_split(filename_out, y8, w, h, pd);
+		free(x);
+		free(y8);
+		return 0;
+	}
 
 	/* The reference reads with iio_read_image_float_split (src/morsi.c:531): a
 	 * "vec" read followed by a CPU pass that splits the pixels into planes

@@ -350,3 +350,85 @@ extern "C" int morsi_cuda_apply_stream(int op, const int *e, int w, int h, int p
 	cleanup();
 	return rc;
 }
+
+// ---------------------------------------------------------------------------
+// pipe chains: `morsi E1 OP1 in | morsi E2 OP2 | qeasy black white - out.png`
+// ---------------------------------------------------------------------------
+// doc/tutorial/i.html:221-225 pipes morsi into qeasy (src/qeasy.c:55-73), scripts pipe
+// morsi into morsi: every `|` is a full serialisation of the image and, here, a PCIe round
+// trip.  The chain runs on the device instead: one upload, the operations ping-pong between
+// two resident buffers, the quantiser of qeasy is the last kernel, and an 8-bit result
+// crosses PCIe as bytes.
+//   x[i] = floor(255 * (x[i] - black) / (white - black))       src/qeasy.c:57-58 (float arithmetic, left to right)
+//   u8:  < 0 -> 0, > 255 -> 255, else the integer value         :64-69 (NaN -> 0, what x86's cvttss2si leaves in the low byte)
+__global__ void __launch_bounds__(256) k_qeasy(const float *in, float *out_f, unsigned char *out_u8, long long n, float black, float white)
+{
+	const float range = __fsub_rn(white, black);
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		const float v = floorf(__fdiv_rn(__fmul_rn(255.0f, __fsub_rn(in[i], black)), range));
+		if (out_f) out_f[i] = v;
+		if (out_u8) out_u8[i] = v < 0.f ? 0 : v > 255.f ? 255 : (v == v ? (unsigned char)(int)v : 0);
+	}
+}
+
+extern "C" int morsi_cuda_apply_chain(int nops, const int *ops, const int *const *elements, const float *x, void *y,
+		int w, int h, int planes, const morsi_quantizer *q)
+{
+	if (nops < 1 || !ops || !elements) return morsi_set_error(MORSI_ERR_INVALID, "chain: no operations");
+	for (int k = 0; k < nops; k++) {
+		if (ops[k] < 0 || ops[k] >= MORSI_OP_COUNT) return morsi_set_error(MORSI_ERR_INVALID, "chain: unknown operation %d", ops[k]);
+		if (!elements[k] || elements[k][0] < 0) return morsi_set_error(MORSI_ERR_INVALID, "chain: bad structuring element %d", k);
+	}
+	if (!x || !y) return morsi_set_error(MORSI_ERR_INVALID, "NULL image pointer");
+	if (w <= 0 || h <= 0 || planes <= 0) return morsi_set_error(MORSI_ERR_INVALID, "non-positive image size %dx%dx%d", w, h, planes);
+	MorsiCtx *c;
+	int rc = morsi_ctx_current(&c);
+	if (rc) return rc;
+	std::lock_guard<std::mutex> host_lk(c->host_mu);
+	const size_t plane_bytes = (size_t)w * h * sizeof(float);
+	size_t free_b = 0, total_b = 0;
+	MORSI_CU(cudaMemGetInfo(&free_b, &total_b));
+	long long pg = (long long)((free_b * 7 / 10) / (3 * plane_bytes));       // two ping-pong buffers + the quantised result
+	if (pg < 1) return morsi_set_error(MORSI_ERR_TOO_LARGE, "chain: three buffers of one %dx%d plane do not fit the device", w, h);
+	if (pg > planes) pg = planes;
+	const bool to_u8 = q && q->to_uint8;
+	cudaStream_t s_run = c->lane_stream[1], s_copy = c->lane_stream[2];
+	void *slab = nullptr;
+	MORSI_CU(cudaMalloc(&slab, 3 * (size_t)pg * plane_bytes));
+	float *buf[2] = {(float *)slab, (float *)slab + (size_t)pg * w * h};
+	void *d_q = (float *)slab + 2 * (size_t)pg * w * h;
+	cudaEvent_t done, copied;
+	cudaEventCreateWithFlags(&done, cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&copied, cudaEventDisableTiming);
+	for (int p0 = 0; p0 < planes && !rc; p0 += (int)pg) {
+		const int np = planes - p0 < pg ? planes - p0 : (int)pg;
+		const long long n = (long long)np * w * h;
+		if (p0 > 0) cudaStreamWaitEvent(s_run, copied, 0);
+		if (cudaMemcpyAsync(buf[0], x + (size_t)p0 * w * h, (size_t)n * 4, cudaMemcpyHostToDevice, s_run) != cudaSuccess) { rc = morsi_set_error(MORSI_ERR_CUDA, "chain: upload"); break; }
+		int cur = 0;
+		for (int k = 0; k < nops && !rc; k++, cur ^= 1)
+			rc = one_pass(c, elements[k], ops[k], buf[cur], buf[cur ^ 1], w, h, np, 1, s_run);
+		if (rc) break;
+		const void *src = buf[cur];
+		size_t out_bytes = (size_t)n * 4;
+		if (q) {
+			k_qeasy<<<c->sm_count * 8, 256, 0, s_run>>>(buf[cur], to_u8 ? nullptr : (float *)d_q, to_u8 ? (unsigned char *)d_q : nullptr, n, q->black, q->white);
+			morsi_count_launch(1);
+			src = d_q;
+			if (to_u8) out_bytes = (size_t)n;
+		}
+		cudaEventRecord(done, s_run);
+		cudaStreamWaitEvent(s_copy, done, 0);
+		char *dst = (char *)y + (size_t)p0 * w * h * (to_u8 ? 1 : 4);
+		if (cudaMemcpyAsync(dst, src, out_bytes, cudaMemcpyDeviceToHost, s_copy) != cudaSuccess) { rc = morsi_set_error(MORSI_ERR_CUDA, "chain: download"); break; }
+		cudaEventRecord(copied, s_copy);
+		// the next group's upload overwrites buf[0]: the download of this group must have read its source first
+		if (src == buf[0]) cudaStreamWaitEvent(s_run, copied, 0);
+	}
+	cudaStreamSynchronize(s_run);
+	cudaStreamSynchronize(s_copy);
+	cudaEventDestroy(done); cudaEventDestroy(copied);
+	cudaFree(slab);
+	if (!rc && cudaGetLastError() != cudaSuccess) rc = morsi_set_error(MORSI_ERR_CUDA, "chain: a CUDA call failed");
+	return rc;
+}

@@ -213,6 +213,16 @@ int morsi_shard_destroy(morsi_shard *s);
 int morsi_cuda_apply_sharded(int op, const int *e, const float *x, float *y,
 		int w, int h, int ndev, int iterations);
 
+/* Pipe chains: `morsi E1 OP1 in | morsi E2 OP2 | qeasy black white - out`
+ * (doc/tutorial/i.html:221-225, src/qeasy.c:55-73) as ONE call: one upload, the nops
+ * operations back to back on the device, optionally qeasy's quantiser
+ * floor(255 (v - black) / (white - black)) as the last kernel.  y receives planar
+ * float32 (q == NULL or !q->to_uint8: qeasy -f) or planar uint8 saturated to
+ * [0,255] (to_uint8: the 8-bit image crosses PCIe as bytes). */
+typedef struct morsi_quantizer { float black, white; int to_uint8; } morsi_quantizer;
+int morsi_cuda_apply_chain(int nops, const int *ops, const int *const *elements,
+		const float *x, void *y, int w, int h, int planes, const morsi_quantizer *q);
+
 /* Force a kernel family: 0 = automatic, 1 = order-preserving exact kernels
  * only (the signed-zero-safe path), 2 = fast kernels without the signed-zero
  * re-run (benchmark use).  Also settable with MORSI_CUDA_PATH=auto|exact|fast. */

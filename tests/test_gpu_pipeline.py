@@ -175,3 +175,48 @@ def test_two_host_threads_one_device_and_pageable_buffers():
         crop = o.apply(ops[t][1], e, xs[t][:80])
         assert_same(out[t][:60], crop[:60], f"thread {t}")
         assert_same(out[t], M.apply(ops[t][1], e, xs[t]), f"thread {t} repeat")
+
+
+def qeasy_numpy(x, black, white, to_u8):
+    """src/qeasy.c:57-69 restated: float arithmetic left to right, floor, saturate"""
+    x = x.astype(np.float32)
+    with np.errstate(all="ignore"):
+        v = np.floor((np.float32(255) * (x - np.float32(black))) / (np.float32(white) - np.float32(black))).astype(np.float32)
+        if not to_u8:
+            return v
+        g = np.where(np.isnan(v), 0, np.clip(v, 0, 255)).astype(np.uint8)
+    return g
+
+
+def test_pipe_chain_and_qeasy():
+    """morsi | morsi | qeasy as one call: the operations back to back on the device, the quantiser last"""
+    o = oracle()
+    h, w = 120, 203
+    x = np.stack([M.synth_host(w, h, plane=p, seed=17, dist=2 if p == 1 else 0) * 200 - 50 for p in range(2)]).astype(np.float32)
+    steps = [("opening", o.element("disk3")), ("gradient", o.element("cross")), ("tophat", o.element("disk7"))]
+    want = x
+    for op, e in steps:
+        want = o.apply(op, e, want)
+    assert_same(M.apply_chain(steps, x), want, "chain of three operations")
+    assert_same(M.apply_chain(steps[:1], x, quant=(40, -40, False)), qeasy_numpy(o.apply("opening", steps[0][1], x), 40, -40, False), "qeasy -f")
+    for (b, wh) in [(0, 60), (40, -40), (-10.5, 3.25)]:
+        lap = o.apply("laplacian", o.element("cross"), x)
+        got = M.apply_chain([("laplacian", o.element("cross"))], x, quant=(b, wh, True))
+        assert got.dtype == np.uint8 and np.array_equal(got, qeasy_numpy(lap, b, wh, True)), (b, wh)
+
+
+def test_cli_qeasy_chain(tmp_path):
+    """MORSI_CUDA_QEASY="0 60" morsi cross tophat in out.npy  ==  morsi cross tophat in | qeasy 0 60 - out"""
+    cli = os.path.join(LIBDIR, "morsi")
+    rng = np.random.default_rng(3)
+    x = (rng.random((70, 90, 3), dtype=np.float32) * 255).astype(np.float32)
+    fin, fout = str(tmp_path / "in.npy"), str(tmp_path / "out.npy")
+    np.save(fin, x)
+    env = dict(os.environ, MORSI_CUDA_QEASY="0 60")
+    p = subprocess.run([cli, "cross", "tophat", fin, fout], env=env, capture_output=True)
+    assert p.returncode == 0, p.stderr
+    got = np.load(fout)
+    o = oracle()
+    planes = np.ascontiguousarray(np.moveaxis(x, -1, 0))
+    want = np.moveaxis(qeasy_numpy(o.apply("tophat", o.element("cross"), planes), 0, 60, True), 0, -1)
+    assert got.dtype == np.uint8 and np.array_equal(got.reshape(want.shape), want)
