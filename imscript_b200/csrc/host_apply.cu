@@ -104,7 +104,9 @@ extern "C" int morsi_cuda_apply(int op, const int *e, const float *x, float *y,
 	HostPin pin_x(x, (size_t)w * h * planes * sizeof(float)), pin_y(y, (size_t)w * h * planes * sizeof(float));
 
 	// chunk height: ~32 MiB of input per chunk, at least 8x the halo
-	long long target = (32LL << 20) / ((long long)w * 4);   // 32 MiB: C2 e2e 10.15 vs 9.94 Gpixel/s with 16 MiB (PCIe ceiling of the box: 47.9 GB/s per direction, both busy)
+	long long chunk_mb = 32;                                 // MiB of input per chunk (MORSI_CUDA_CHUNK_MB; measured: profiles/r2_chunk_sweep.txt)
+	if (const char *s = getenv("MORSI_CUDA_CHUNK_MB")) chunk_mb = std::max(1, atoi(s));
+	long long target = (chunk_mb << 20) / ((long long)w * 4);
 	int band = (int)std::max<long long>(std::max(64, 8 * (up + down)), target);
 	if (const char *s = getenv("MORSI_CUDA_CHUNK_ROWS")) band = std::max(1, atoi(s));
 
