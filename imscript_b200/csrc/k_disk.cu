@@ -473,8 +473,16 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 		mbar_arrive_tx(full_in + 8 * slot, K::GROUP_BYTES);
 		tma_load_4d(ring_u32 + slot * K::GROUP_BYTES, &tm, 0, gxb, trow0 + 2 * GP * gi, plane, full_in + 8 * slot);
 	};
+	// Single stage with an epilogue that needs the centre pixel x: the rows of x went through the
+	// ring ceil(R/2) pairs before the output rows complete.  When that is less than a group the
+	// producer runs one group less ahead, the previous group stays intact while the current one is
+	// consumed, and x comes from shared memory instead of a global load whose latency nothing hides
+	// (measured: disk7 igradient of the C2 image 0.160 ms with the global load, erosion alone 0.079).
+	constexpr bool XRING_OK = !TWO && (R + 1) / 2 + 1 <= GP && NG >= 3;
+	const bool xring = XRING_OK && p.xop.p != nullptr && p.xop.p == p.src.p && p.epi != (ISMAX ? EPI_B : EPI_A);
+	const int ahead = xring ? NG - 2 : NG - 1;             // groups the producer runs ahead
 	if (producer) {
-		for (int gi = 0; gi < NG - 1 && gi < ngroups; gi++) load_group(gi);
+		for (int gi = 0; gi < ahead && gi < ngroups; gi++) load_group(gi);
 	}
 
 	// ---- consumer state ----
@@ -509,9 +517,20 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 	const float *oq = (!TWO && p.other.p) ? p.other.p + plane * p.other.pstride + (long long)(Y0 - p.other.row0 - 2 * R) * pitch + x : nullptr;
 	const int epi = p.epi;
 	const bool plain = epi == (ISMAX ? EPI_B : EPI_A);                 // single stage only
+	// The one-sided epilogues (src/morsi.c:174,183,252,261) are all y = ec * (ep * x + eq * m) with
+	// ep, eq = +-1 and ec = 1 or 0.5: products by +-1 and by 0.5 are exact, so the three roundings are
+	// the reference's, and the epilogue is three FMA-pipe instructions instead of an out-of-line switch.
+	float ec = 1.f, ep = 1.f, eq = 1.f;
+	bool linear = false;
+	if (!TWO) {
+		if (epi == EPI_X_SUB_A) { linear = true; eq = -1.f; }                       // x - a
+		if (epi == EPI_B_SUB_X) { linear = true; ep = -1.f; }                       // b - x
+		if (epi == EPI_IBLUR || epi == EPI_EBLUR) { linear = true; ec = 0.5f; }     // (x + m) / 2
+	}
 	int gi = 0;                                                        // group being consumed
 	const float *grp = my_ring;                                        // ... and this thread's window in it
-	unsigned grp_empty = my_empty;
+	const float *grp_prev = my_ring;                                   // the group before it (xring)
+	unsigned grp_empty = my_empty, grp_empty_prev = my_empty;
 	int tgi = 0;                                                       // first stage: temporary group being written
 	float *tgrp = my_tmp;
 	unsigned tgrp_full = full_t;
@@ -526,8 +545,9 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 				if (pos == 0) {
 					// a new group: keep the producer one group ahead, then wait for ours
 					const int slot = gi % NG;
-					if (producer && gi + NG - 1 < ngroups) load_group(gi + NG - 1);
+					if (producer && gi + ahead < ngroups) load_group(gi + ahead);
 					mbar_wait_warp(my_full + 8 * slot, (gi / NG) & 1);
+					grp_prev = grp; grp_empty_prev = grp_empty;
 					grp = my_ring + slot * GROUP;
 					grp_empty = my_empty + 8 * slot;
 					gi++;
@@ -547,8 +567,22 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 					// operands of the epilogue, in flight during the reductions below
 #pragma unroll
 					for (int c = 0; c < C; c++) { xv0[c] = 0.f; xv1[c] = 0.f; ov0[c] = 0.f; ov1[c] = 0.f; }
-					if (e0 && xq) load_cols<C>(xq, xv0);
-					if (e1 && xq) load_cols<C>(xq + pitch, xv1);
+					if (XRING_OK && xring) {
+						// output rows o0, o0+1 are input rows 2g-R, 2g-R+1 of the band: pair g - ceil(R/2) (row B
+						// of it and row A of the next one when R is odd), at most one group back
+						const int back = (R + 1) / 2;
+						const int pa = (pos - back + GP) % GP;                  // place of the first row's pair in its group
+						const float *ga = pos >= back ? grp : grp_prev;
+						const int pb = R % 2 ? (pos - back + 1 + GP) % GP : pa;
+						const float *gb = R % 2 ? (pos >= back - 1 ? grp : grp_prev) : ga;
+						const float *xa = ga + pa * PAIR + (R % 2 ? RP : 0) + LH;
+						const float *xb2 = gb + pb * PAIR + (R % 2 ? 0 : RP) + LH;
+#pragma unroll
+						for (int c = 0; c < C; c++) { xv0[c] = xa[c]; xv1[c] = xb2[c]; }
+					} else {
+						if (e0 && xq) load_cols<C>(xq, xv0);
+						if (e1 && xq) load_cols<C>(xq + pitch, xv1);
+					}
 					if (e0 && oq) load_cols<C>(oq, ov0);
 					if (e1 && oq) load_cols<C>(oq + pitch, ov1);
 				}
@@ -559,7 +593,11 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 #endif
 					// the group has been read (its loads were issued before this
 					// arrive and complete long before a refill can land)
-					[&]() { if (pos == GP - 1 && lane0) mbar_arrive(grp_empty); },
+					// xring: a group stays in use, as the source of x, for ceil(R/2) steps into the next one
+					[&]() {
+						if (XRING_OK && xring) { if (pos == (R + 1) / 2 && lane0 && gi >= 2) mbar_arrive(grp_empty_prev); }
+						else if (pos == GP - 1 && lane0) mbar_arrive(grp_empty);
+					},
 					[&](const float (&m0)[C], const float (&m1)[C]) {
 					if (first) {
 						// temporary pair tp = g-R: rows T0+2tp, T0+2tp+1 (T0 = Y0-R), stored negated
@@ -609,7 +647,12 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 					} else {
 						if (e0) {
 							if (plain) store_cols<C>(yq, m0);
-							else {
+							else if (linear) {
+								float r[C];
+#pragma unroll
+								for (int c = 0; c < C; c++) r[c] = __fmul_rn(ec, __fadd_rn(__fmul_rn(ep, xv0[c]), __fmul_rn(eq, m0[c])));
+								store_cols<C>(yq, r);
+							} else {
 								const float4 r = disk_epi4<ISMAX>(epi, m0[0], m0[1], C == 4 ? m0[2] : 0.f, C == 4 ? m0[3] : 0.f,
 										ov0[0], ov0[1], C == 4 ? ov0[2] : 0.f, C == 4 ? ov0[3] : 0.f,
 										xv0[0], xv0[1], C == 4 ? xv0[2] : 0.f, C == 4 ? xv0[3] : 0.f);
@@ -618,7 +661,12 @@ k_disk(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 						}
 						if (e1) {
 							if (plain) store_cols<C>(yq + pitch, m1);
-							else {
+							else if (linear) {
+								float r[C];
+#pragma unroll
+								for (int c = 0; c < C; c++) r[c] = __fmul_rn(ec, __fadd_rn(__fmul_rn(ep, xv1[c]), __fmul_rn(eq, m1[c])));
+								store_cols<C>(yq + pitch, r);
+							} else {
 								const float4 r = disk_epi4<ISMAX>(epi, m1[0], m1[1], C == 4 ? m1[2] : 0.f, C == 4 ? m1[3] : 0.f,
 										ov1[0], ov1[1], C == 4 ? ov1[2] : 0.f, C == 4 ? ov1[3] : 0.f,
 										xv1[0], xv1[1], C == 4 ? xv1[2] : 0.f, C == 4 ? xv1[3] : 0.f);
@@ -888,7 +936,7 @@ template <class S, int C, int W>
 struct DiskCfgDual {
 	using K1 = DiskCfg<S, C, W, false>;
 	static constexpr int R = K1::R, LH = K1::LH, NT = K1::NT, TW = K1::TW, OUTW = K1::OUTW, RP = K1::RP;
-	static constexpr int PERIOD = K1::PERIOD, GP = K1::GP, PAIR = K1::PAIR, GROUP = K1::GROUP, NG = 2;
+	static constexpr int PERIOD = K1::PERIOD, GP = K1::GP, PAIR = K1::PAIR, GROUP = K1::GROUP, NG = 3;
 	static constexpr unsigned GROUP_BYTES = K1::GROUP_BYTES;
 	static constexpr int NACC = K1::NACC;
 	static constexpr int THREADS = NT;
@@ -897,7 +945,8 @@ struct DiskCfgDual {
 	static constexpr bool OK = 2 * C * (2 * R + 2) <= 112;     // the accumulators of both flavours fit the register file
 };
 
-template <class S, int C, int W>
+// EPI: the epilogue, compile time (a run-time switch in an out-of-line call cost 15 % of the samples here)
+template <class S, int C, int W, int EPI>
 __global__ void __launch_bounds__(DiskCfgDual<S, C, W>::THREADS, DiskCfgDual<S, C, W>::MINB)
 k_disk_dual(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 {
@@ -942,8 +991,11 @@ k_disk_dual(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 		mbar_arrive_tx(full_in + 8 * slot, K::GROUP_BYTES);
 		tma_load_4d(ring_u32 + slot * K::GROUP_BYTES, &tm, 0, gxb, trow0 + 2 * GP * gl, plane, full_in + 8 * slot);
 	};
+	// epilogues with the centre pixel take it from the ring (see k_disk): the producer then runs one group ahead
+	constexpr bool XRING = EpiNeeds<EPI>::x && (R + 1) / 2 + 1 <= GP;
+	constexpr int AHEAD = XRING ? NG - 2 : NG - 1;
 	if (tid == 0) {
-		for (int gl = 0; gl < NG - 1 && gl < ngroups; gl++) load_group(gl);
+		for (int gl = 0; gl < AHEAD && gl < ngroups; gl++) load_group(gl);
 	}
 
 	float accA[C][K::NACC], hsA[C][4], accB[C][K::NACC], hsB[C][4];
@@ -962,10 +1014,9 @@ k_disk_dual(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 	const bool pad_edge = col_ok && x + C > w;
 	float *yq = p.y + plane * p.y_pstride + (long long)(Y0 - p.y_row0 - 2 * R) * pitch + x;
 	const float *xq = p.xop.p ? p.xop.p + plane * p.xop.pstride + (long long)(Y0 - p.xop.row0 - 2 * R) * pitch + x : nullptr;
-	const int epi = p.epi;
 	int gi = 0;
-	const float *grp = my_ring;
-	unsigned grp_empty = empty_in;
+	const float *grp = my_ring, *grp_prev = my_ring;
+	unsigned grp_empty = empty_in, grp_empty_prev = empty_in;
 
 #pragma unroll 1
 	for (int g0 = 0; g0 < G2; g0 += PERIOD) {
@@ -976,8 +1027,9 @@ k_disk_dual(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 				const int pos = s % GP;
 				if (pos == 0) {
 					const int slot = gi % NG;
-					if (tid == 0 && gi + NG - 1 < ngroups) load_group(gi + NG - 1);
+					if (tid == 0 && gi + AHEAD < ngroups) load_group(gi + AHEAD);
 					mbar_wait_warp(full_in + 8 * slot, (gi / NG) & 1);
+					grp_prev = grp; grp_empty_prev = grp_empty;
 					grp = my_ring + slot * GROUP;
 					grp_empty = empty_in + 8 * slot;
 					gi++;
@@ -989,8 +1041,20 @@ k_disk_dual(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 				float xv0[C], xv1[C], a0[C], a1[C];
 #pragma unroll
 				for (int c = 0; c < C; c++) { xv0[c] = 0.f; xv1[c] = 0.f; }
-				if (e0 && xq) load_cols<C>(xq, xv0);
-				if (e1 && xq) load_cols<C>(xq + pitch, xv1);
+				if (XRING) {
+					const int back = (R + 1) / 2;
+					const int pa = (pos - back + GP) % GP;
+					const float *ga = pos >= back ? grp : grp_prev;
+					const int pb = R % 2 ? (pos - back + 1 + GP) % GP : pa;
+					const float *gb = R % 2 ? (pos >= back - 1 ? grp : grp_prev) : ga;
+					const float *xa = ga + pa * PAIR + (R % 2 ? RP : 0) + LH;
+					const float *xb2 = gb + pb * PAIR + (R % 2 ? 0 : RP) + LH;
+#pragma unroll
+					for (int c = 0; c < C; c++) { xv0[c] = xa[c]; xv1[c] = xb2[c]; }
+				} else if (EpiNeeds<EPI>::x) {
+					if (e0) load_cols<C>(xq, xv0);
+					if (e1) load_cols<C>(xq + pitch, xv1);
+				}
 				Dmin::step(accA, hsA, s % (R + 1), rowA, rowA + RP, zmin, true,
 					[]() {},
 					[&](const float (&m0)[C], const float (&m1)[C]) {
@@ -998,19 +1062,22 @@ k_disk_dual(const __grid_constant__ CUtensorMap tm, DiskArgs p, int bw)
 						for (int c = 0; c < C; c++) { a0[c] = m0[c]; a1[c] = m1[c]; }
 					});
 				Dmax::step(accB, hsB, s % (R + 1), rowA, rowA + RP, zdummy, false,
-					[&]() { if (pos == GP - 1 && lane0) mbar_arrive(grp_empty); },
+					[&]() {
+						if (XRING) { if (pos == (R + 1) / 2 && lane0 && gi >= 2) mbar_arrive(grp_empty_prev); }
+						else if (pos == GP - 1 && lane0) mbar_arrive(grp_empty);
+					},
 					[&](const float (&m0)[C], const float (&m1)[C]) {
 					if (e0) {
-						const float4 r = disk_epi4<true>(epi, m0[0], m0[1], C == 4 ? m0[2] : 0.f, C == 4 ? m0[3] : 0.f,
-								a0[0], a0[1], C == 4 ? a0[2] : 0.f, C == 4 ? a0[3] : 0.f,
-								xv0[0], xv0[1], C == 4 ? xv0[2] : 0.f, C == 4 ? xv0[3] : 0.f);
-						if (C == 4) *(float4 *)yq = r; else *(float2 *)yq = make_float2(r.x, r.y);
+						float r[C];
+#pragma unroll
+						for (int c = 0; c < C; c++) r[c] = epilogue<EPI>(a0[c], m0[c], xv0[c]);
+						store_cols<C>(yq, r);
 					}
 					if (e1) {
-						const float4 r = disk_epi4<true>(epi, m1[0], m1[1], C == 4 ? m1[2] : 0.f, C == 4 ? m1[3] : 0.f,
-								a1[0], a1[1], C == 4 ? a1[2] : 0.f, C == 4 ? a1[3] : 0.f,
-								xv1[0], xv1[1], C == 4 ? xv1[2] : 0.f, C == 4 ? xv1[3] : 0.f);
-						if (C == 4) *(float4 *)(yq + pitch) = r; else *(float2 *)(yq + pitch) = make_float2(r.x, r.y);
+						float r[C];
+#pragma unroll
+						for (int c = 0; c < C; c++) r[c] = epilogue<EPI>(a1[c], m1[c], xv1[c]);
+						store_cols<C>(yq + pitch, r);
 					}
 					if (pad_edge) {
 #pragma unroll
@@ -1184,17 +1251,17 @@ static int disk_launch_both(const MorsiCtx *c, const DiskArgs &a0, int planes, c
 	return MORSI_OK;
 }
 
-template <class S, int C, int W>
-static int disk_launch_dual(const MorsiCtx *c, const DiskArgs &a0, int planes, cudaStream_t st)
+template <class S, int C, int W, int EPI>
+static int disk_launch_dual_e(const MorsiCtx *c, const DiskArgs &a0, int planes, cudaStream_t st)
 {
 	using K = DiskCfgDual<S, C, W>;
 	DiskArgs a = a0;
 	static int occs[64];
 	int &occ = occs[c->device & 63];
 	if (occ <= 0) {
-		cudaFuncSetAttribute(k_disk_dual<S, C, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
+		cudaFuncSetAttribute(k_disk_dual<S, C, W, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K::SMEM);
 		int o = 0;
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_disk_dual<S, C, W>, K::THREADS, K::SMEM) != cudaSuccess || o < 1) o = 1;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_disk_dual<S, C, W, EPI>, K::THREADS, K::SMEM) != cudaSuccess || o < 1) o = 1;
 		occ = o;
 	}
 	const int strips = (a.w + K::OUTW - 1) / K::OUTW;
@@ -1204,10 +1271,24 @@ static int disk_launch_dual(const MorsiCtx *c, const DiskArgs &a0, int planes, c
 	int rc = disk_tensor_map(&tm, a.src, a.src_rows, a.pitch, planes, K::RP, 2 * K::GP, &bw);
 	if (rc) return rc;
 	dim3 grid(strips, (a.y_rows + a.band_rows - 1) / a.band_rows, planes);
-	k_disk_dual<S, C, W><<<grid, K::THREADS, K::SMEM, st>>>(tm, a, bw);
+	k_disk_dual<S, C, W, EPI><<<grid, K::THREADS, K::SMEM, st>>>(tm, a, bw);
 	morsi_count_launch(1);
 	MORSI_CU(cudaGetLastError());
 	return MORSI_OK;
+}
+
+// -1: not an epilogue of the gradient family (the caller takes another kernel)
+template <class S, int C, int W>
+static int disk_launch_dual(const MorsiCtx *c, const DiskArgs &a, int planes, cudaStream_t st)
+{
+	switch (a.epi) {
+	case EPI_B_SUB_A: return disk_launch_dual_e<S, C, W, EPI_B_SUB_A>(c, a, planes, st);
+	case EPI_LAP: return disk_launch_dual_e<S, C, W, EPI_LAP>(c, a, planes, st);
+	case EPI_ENH: return disk_launch_dual_e<S, C, W, EPI_ENH>(c, a, planes, st);
+	case EPI_BLUR: return disk_launch_dual_e<S, C, W, EPI_BLUR>(c, a, planes, st);
+	case EPI_CBLUR: return disk_launch_dual_e<S, C, W, EPI_CBLUR>(c, a, planes, st);
+	}
+	return -1;
 }
 
 static int disk_forced_w()
@@ -1240,7 +1321,10 @@ static int disk_shape_c(MorsiCtx *c, const DiskArgs &a, int planes, bool ismax, 
 		// both reductions in every thread where the register file holds them (R <= 6; MORSI_DISK_DUAL=0: the two-role kernel)
 		static const bool no_dual = getenv("MORSI_DISK_DUAL") && !strcmp(getenv("MORSI_DISK_DUAL"), "0");
 		if (DiskCfgDual<S, C, 2>::OK && !no_dual) {
-			if constexpr (DiskCfgDual<S, C, 2>::OK) return disk_launch_dual<S, C, 2>(c, a, planes, st);
+			if constexpr (DiskCfgDual<S, C, 2>::OK) {
+				const int rc = disk_launch_dual<S, C, 2>(c, a, planes, st);
+				if (rc != -1) return rc;
+			}
 		}
 		// 2 warps per role for the small disks, 4 for the ones that need every register
 		if (disk_forced_w() == 4 || (disk_forced_w() != 2 && DiskCfgBoth<S, C, 2>::REGS >= 255))
