@@ -437,7 +437,17 @@ def measure_sharded(env, steps, warmup, with_e2e=True):
     element, ops, w, h, planes, seed, desc = WORKLOADS["c4"]
     e = M.parse_element(element)
     op = M.OPS.index(ops[0])
-    job = shard.ShardJob(L, op, e, w, h, env.rank, env.world, env.local, env.dist, seed)
+    # every rank must agree that the sharded plane exists before anyone waits for a neighbour
+    job, err = None, ""
+    try:
+        job = shard.ShardJob(L, op, e, w, h, env.rank, env.world, env.local, env.dist, seed)
+    except Exception as ex:                      # e.g. no peer access / CUDA IPC between the ranks' devices
+        err = str(ex)[:300]
+    if env.max_over_ranks(0.0 if job is not None else 1.0) > 0:
+        if job is not None:
+            job.destroy()
+        return {"workload": desc, "n_gpus": env.world, "scaling": "strong",
+                "error": err or "another rank could not create or connect its shard"}
     sync = job.sync
     ms_per_step, launches, clocks = env.timed(job.step, job.stream, steps, warmup, sync)
     halo = int(env.sum_over_ranks(job.halo_bytes()))
@@ -492,6 +502,8 @@ def main_ours(args):
     sharded_rec = None
     if name == "c4":
         sharded_rec = measure_sharded(env, args.steps, args.warmup)
+        if "error" in sharded_rec:
+            raise SystemExit("bench.py: the sharded workload could not be set up: " + sharded_rec["error"])
         main = {"ms_per_step": sharded_rec["ms_per_step"], "launches": sharded_rec["gpu_launches"],
                 "clocks": sharded_rec["clocks"], "e2e": sharded_rec.get("e2e"), "samples_total": w * h * len(ops),
                 "scaling": "strong"}

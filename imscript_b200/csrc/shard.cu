@@ -207,16 +207,21 @@ extern "C" int morsi_shard_create(morsi_shard **out, int device, int rank, int n
 	s->timeout_ms = tm ? (unsigned)atoi(tm) : 20000u;
 	cudaError_t e = cudaMalloc(&s->slab, s->slab_bytes);
 	if (e != cudaSuccess) {
+		const size_t want = s->slab_bytes;
 		delete s;
-		return morsi_set_error(MORSI_ERR_OOM, "shard_create: %zu bytes on device %d: %s", s->slab_bytes, device, cudaGetErrorString(e));
+		return morsi_set_error(MORSI_ERR_OOM, "shard_create: %zu bytes on device %d: %s", want, device, cudaGetErrorString(e));
 	}
-	SH_CU(cudaMemset(s->slab, 0, SHARD_FLAG_BYTES));
-	SH_CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-	SH_CU(cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
-	SH_CU(cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
-	SH_CU(cudaStreamCreateWithFlags(&s->s_comm, cudaStreamNonBlocking));
-	SH_CU(cudaStreamCreateWithFlags(&s->s_side, cudaStreamNonBlocking));
-	for (int i = 0; i < 4; i++) SH_CU(cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming));
+	cudaError_t ce = cudaMemset(s->slab, 0, SHARD_FLAG_BYTES);
+	cudaStream_t *streams[5] = {&s->stream, &s->s_in, &s->s_out, &s->s_comm, &s->s_side};
+	for (int i = 0; i < 5; i++) { *streams[i] = nullptr; if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(streams[i], cudaStreamNonBlocking); }
+	for (int i = 0; i < 4; i++) { s->ev[i] = nullptr; if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming); }
+	if (ce != cudaSuccess) {
+		for (int i = 0; i < 5; i++) if (*streams[i]) cudaStreamDestroy(*streams[i]);
+		for (int i = 0; i < 4; i++) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+		cudaFree(s->slab);
+		delete s;
+		return morsi_set_error(MORSI_ERR_CUDA, "shard_create: %s", cudaGetErrorString(ce));
+	}
 	*out = s;
 	return MORSI_OK;
 }

@@ -6,16 +6,16 @@ timeout 1500 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest_
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c2.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-sharded > gpurun_out/ncu_launch.log 2>&1
 cap() {  # name regex skip command...
   local name=$1 re=$2 skip=$3; shift 3
-  timeout 400 ncu --set full --clock-control none --import-source on -k regex:$re -s $skip -c 1 -o /tmp/$name -f "$@" > gpurun_out/ncu_$name.log 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k "regex:$re" -s $skip -c 1 -o /tmp/$name -f "$@" > gpurun_out/ncu_$name.log 2>&1
   ncu -i /tmp/$name.ncu-rep --page raw --csv > gpurun_out/${name}_raw.csv 2>/dev/null
   ncu -i /tmp/$name.ncu-rep --page source --csv > gpurun_out/${name}_source.csv 2>/dev/null
   python scratch/ncu_summary.py /tmp/$name.ncu-rep > gpurun_out/${name}_summary.txt 2>&1
   head -3 gpurun_out/${name}_summary.txt
 }
-cap kdisk_c2 'k_disk<' 4 python scratch/time_op.py disk7 opening 4096 4096 3 0 3
-cap kdisk_c4 'k_disk<' 3 python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu
+cap kdisk_c2 '^k_disk$' 4 python scratch/time_op.py disk7 opening 4096 4096 3 0 3
+cap kdisk_c4 '^k_disk$' 3 python bench.py --workload c4 --steps 1 --warmup 3 --no-cpu
 cap kmedian_c3 k_median_quad 3 python bench.py --workload c3 --steps 1 --warmup 3 --no-cpu --no-sharded
-cap kboth_disk7 k_disk_both 4 python scratch/time_op.py disk7 gradient 4096 4096 3 0 3
+cap kdual_disk7 '^k_disk_dual$' 4 python scratch/time_op.py disk7 gradient 4096 4096 3 0 3
 cap kruns_disk20 k_runs 4 python scratch/time_op.py disk20 erosion 4096 4096 3 0 3
 cap ksmall_c5 k_small 3 python bench.py --workload c5 --steps 1 --warmup 3 --no-cpu --no-sharded
 python scratch/make_traffic.py c2=kdisk_c2 c4=kdisk_c4 c3=kmedian_c3 c5=ksmall_c5
