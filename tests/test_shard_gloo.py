@@ -81,3 +81,54 @@ def test_band_plan_covers_image_and_edges():
             assert len(sends) == len(recvs) == (p.rank > 0) + (p.rank < world - 1)
             assert sum(t[3] for t in recvs) == p.rows_held - p.rows_own
     assert not BandPlan(40, 1, 4, 28, 28).halo_complete()
+
+
+def _handle_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from imscript_b200 import shard
+        from imscript_b200.binding import SHARD_HANDLE_BYTES
+        mine = bytes([rank + 1]) * SHARD_HANDLE_BYTES          # stands in for morsi_shard_handle()'s 128 bytes
+        table = shard.gather_handles(mine, dist, world)
+        ok = len(table) == world * SHARD_HANDLE_BYTES and \
+            all(table[r * SHARD_HANDLE_BYTES:(r + 1) * SHARD_HANDLE_BYTES] == bytes([r + 1]) * SHARD_HANDLE_BYTES
+                for r in range(world))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_handles_are_gathered_in_rank_order():
+    """the one piece of plumbing the C-level sharded path leaves to the caller: every rank ends up with the
+    nranks x 128-byte handle table in rank order (world_size 3 over gloo)"""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_handle_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results == [(r, True) for r in range(world)]
+
+
+def test_band_plan_matches_the_c_bookkeeping():
+    """BandPlan restates morsi_shard_create / shard_push (shard.cu): owned rows h*r/N, held rows clipped to the
+    image, the rows pushed to a neighbour are the first `down` / last `up` owned rows"""
+    for (h, world, halo) in [(40000, 8, 28), (3001, 2, 28), (3001, 4, 12), (100, 3, 0)]:
+        prev_b1 = 0
+        for r in range(world):
+            p = BandPlan(h, r, world, halo, halo)
+            assert p.b0 == h * r // world == prev_b1 and p.b1 == h * (r + 1) // world
+            assert p.i0 == max(0, p.b0 - halo) and p.i1 == min(h, p.b1 + halo)
+            sends = {peer: (r0, n) for kind, peer, r0, n in p.transfers() if kind == "send"}
+            if r > 0 and halo:
+                assert sends[r - 1] == (p.own_offset, min(halo, p.rows_own))
+            if r < world - 1 and halo:
+                assert sends[r + 1] == (p.own_offset + p.rows_own - min(halo, p.rows_own), min(halo, p.rows_own))
+            prev_b1 = p.b1
+        assert prev_b1 == h
