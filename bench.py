@@ -462,6 +462,7 @@ def measure_sharded(env, steps, warmup, with_e2e=True):
     rec = {"workload": desc, "n_gpus": env.world, "scaling": "strong", "ms_per_step": ms_per_step,
            "value": samples / (ms_per_step * 1e-3) / 1e6, "unit": "Mpixel/s", "steps": steps, "warmup": warmup,
            "rows_per_rank": job.plan.rows_own, "halo_rows": [up, down],
+           "l2": "every rank reads and writes %.1f GB per step: far beyond the 126 MB L2" % (2 * job.plan.rows_own * w * 4 / 1e9),
            "halo_bytes_per_step_all_ranks": halo, "exchange_us": None if ex_ms is None else ex_ms * 1e3,
            "exchange": "libmorsi_cuda: remote stores into the neighbours' halo rows over NVLink (CUDA IPC), "
                        "device-side credit/ready flags, interior rows overlap the transfer" if env.world > 1
